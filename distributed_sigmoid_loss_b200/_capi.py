@@ -1,0 +1,124 @@
+"""ctypes binding of the C ABI declared in include/siglip_b200.h.
+
+The shared library is built in-tree (``make -C distributed_sigmoid_loss_b200/csrc`` or
+``__graft_entry__.build()``) and loaded from the package directory. There is no fallback: if the
+library is missing or no sm_100 device is visible, the product path raises.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import subprocess
+from typing import Optional
+
+_PKG_DIR = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_PKG_DIR, "libsiglip_b200.so")
+CSRC_DIR = os.path.join(_PKG_DIR, "csrc")
+
+# every symbol include/siglip_b200.h declares (tests check the .so exports all of them)
+EXPORTED_SYMBOLS = (
+    "siglip_version",
+    "siglip_last_error",
+    "siglip_device_count",
+    "siglip_ctx_create",
+    "siglip_ctx_set_option",
+    "siglip_ctx_workspace_bytes",
+    "siglip_ctx_handle_bytes",
+    "siglip_ctx_export_handles",
+    "siglip_ctx_import_handles",
+    "siglip_fwd_bwd",
+    "siglip_fwd",
+    "siglip_fwd_bwd_host",
+    "siglip_ctx_launch_count",
+    "siglip_debug_gemm",
+    "siglip_ctx_destroy",
+)
+
+SIGLIP_OK = 0
+SIGLIP_ERR_INVALID = 1
+SIGLIP_ERR_CUDA = 2
+SIGLIP_ERR_NO_DEVICE = 3
+SIGLIP_ERR_STATE = 4
+
+SIGLIP_OPT_CTA_GROUP = 1
+SIGLIP_OPT_OVERLAP_PULL = 2
+
+_lib: Optional[ctypes.CDLL] = None
+
+
+class SiglipError(RuntimeError):
+    """A C-ABI call returned a non-zero status."""
+
+    def __init__(self, code: int, message: str):
+        super().__init__(f"siglip_b200 error {code}: {message}")
+        self.code = code
+
+
+def build(force: bool = False) -> str:
+    """Compile the CUDA extension for sm_100a with nvcc (cross-compiles without a GPU)."""
+    if force and os.path.exists(LIB_PATH):
+        os.remove(LIB_PATH)
+    subprocess.run(["make", "-C", CSRC_DIR], check=True, capture_output=True, text=True)
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(f"build did not produce {LIB_PATH}")
+    return LIB_PATH
+
+
+def lib() -> ctypes.CDLL:
+    """Load (once) and type the shared library. Raises if it is not there."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} is missing: build it with `make -C {CSRC_DIR}` (or __graft_entry__.build()). "
+            "distributed_sigmoid_loss_b200 has no CPU / PyTorch fallback."
+        )
+    L = ctypes.CDLL(LIB_PATH)
+    vp, ci, cs = ctypes.c_void_p, ctypes.c_int, ctypes.c_size_t
+    L.siglip_version.restype = ctypes.c_char_p
+    L.siglip_last_error.restype = ctypes.c_char_p
+    L.siglip_device_count.restype = ci
+    L.siglip_ctx_create.argtypes = [ctypes.POINTER(vp), ci, ci, ci, ci, ci]
+    L.siglip_ctx_create.restype = ci
+    L.siglip_ctx_set_option.argtypes = [vp, ci, ci]
+    L.siglip_ctx_set_option.restype = ci
+    L.siglip_ctx_workspace_bytes.argtypes = [vp]
+    L.siglip_ctx_workspace_bytes.restype = cs
+    L.siglip_ctx_handle_bytes.restype = cs
+    L.siglip_ctx_export_handles.argtypes = [vp, vp, cs]
+    L.siglip_ctx_export_handles.restype = ci
+    L.siglip_ctx_import_handles.argtypes = [vp, vp, cs]
+    L.siglip_ctx_import_handles.restype = ci
+    L.siglip_fwd_bwd.argtypes = [vp] * 11
+    L.siglip_fwd_bwd.restype = ci
+    L.siglip_fwd.argtypes = [vp] * 7
+    L.siglip_fwd.restype = ci
+    L.siglip_fwd_bwd_host.argtypes = [vp, vp, vp, ctypes.c_float, ctypes.c_float, vp, vp, vp, vp, vp, vp]
+    L.siglip_fwd_bwd_host.restype = ci
+    L.siglip_ctx_launch_count.argtypes = [vp]
+    L.siglip_ctx_launch_count.restype = ctypes.c_ulonglong
+    L.siglip_debug_gemm.argtypes = [ci, ci, ci, ci, ci, vp, ctypes.c_longlong, ci, vp, ctypes.c_longlong, ci, vp,
+                                    ctypes.c_longlong, vp]
+    L.siglip_debug_gemm.restype = ci
+    L.siglip_ctx_destroy.argtypes = [vp]
+    L.siglip_ctx_destroy.restype = None
+    _lib = L
+    return L
+
+
+def last_error() -> str:
+    return lib().siglip_last_error().decode("utf-8", "replace")
+
+
+def check(code: int) -> None:
+    if code != SIGLIP_OK:
+        raise SiglipError(code, last_error())
+
+
+def device_count() -> int:
+    return int(lib().siglip_device_count())
+
+
+def version() -> str:
+    return lib().siglip_version().decode()

@@ -1,0 +1,618 @@
+// C ABI (include/siglip_b200.h) over the sm_100a kernels: context + workspaces, TMA descriptor encoding,
+// the per-step chunk schedule, CUDA-IPC peer bootstrap. Host-side only; no torch types anywhere.
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/siglip_b200.h"
+#include "siglip_kernels.cuh"
+
+using siglip::DebugRecord;
+using siglip::KernelParams;
+using siglip::Problem;
+
+namespace {
+
+thread_local std::string g_last_error;
+
+int fail(int code, const std::string& msg) {
+  g_last_error = msg;
+  return code;
+}
+
+#define CK(call)                                                                                       \
+  do {                                                                                                 \
+    cudaError_t e__ = (call);                                                                          \
+    if (e__ != cudaSuccess) {                                                                          \
+      char buf__[512];                                                                                 \
+      snprintf(buf__, sizeof(buf__), "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, \
+               __LINE__);                                                                              \
+      return fail(SIGLIP_ERR_CUDA, buf__);                                                             \
+    }                                                                                                  \
+  } while (0)
+
+#define CKI(expr)                                                                                         \
+  do {                                                                                                    \
+    int e__ = (expr);                                                                                     \
+    if (e__ != 0) {                                                                                       \
+      char buf__[512];                                                                                    \
+      snprintf(buf__, sizeof(buf__), "%s failed: %s (%s:%d)", #expr,                                      \
+               cudaGetErrorString(static_cast<cudaError_t>(e__)), __FILE__, __LINE__);                    \
+      return fail(SIGLIP_ERR_CUDA, buf__);                                                                \
+    }                                                                                                     \
+  } while (0)
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn == nullptr) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess) {
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+  }
+  return fn;
+}
+
+// bf16 2-D tensor, `inner` contiguous elements per row, rows `row_stride_elems` apart; 128B-swizzled boxes.
+int encode_bf16_2d(CUtensorMap* m, const void* base, uint64_t inner, uint64_t outer, uint64_t row_stride_elems,
+                   uint32_t box_inner, uint32_t box_outer) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (fn == nullptr) return fail(SIGLIP_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+  if ((reinterpret_cast<uintptr_t>(base) & 15u) != 0) return fail(SIGLIP_ERR_INVALID, "operand not 16-byte aligned");
+  if ((row_stride_elems * 2) % 16 != 0) return fail(SIGLIP_ERR_INVALID, "row stride not a multiple of 16 bytes");
+  cuuint64_t dims[2] = {inner, outer};
+  cuuint64_t strides[1] = {row_stride_elems * 2};
+  cuuint32_t box[2] = {box_inner, box_outer};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    char buf[256];
+    snprintf(buf, sizeof(buf), "cuTensorMapEncodeTiled failed with CUresult %d (inner=%llu outer=%llu stride=%llu)",
+             static_cast<int>(r), (unsigned long long)inner, (unsigned long long)outer,
+             (unsigned long long)row_stride_elems);
+    return fail(SIGLIP_ERR_CUDA, buf);
+  }
+  return 0;
+}
+
+// Operand tensor map for the mainloop. mn == 0: stored [rows][K]; mn == 1: stored [K][rows].
+int encode_operand(CUtensorMap* m, const void* base, int rows, int K, long long ld, int mn, int box_rows_kmajor) {
+  if (!mn) return encode_bf16_2d(m, base, (uint64_t)K, (uint64_t)rows, (uint64_t)ld, 64, (uint32_t)box_rows_kmajor);
+  return encode_bf16_2d(m, base, (uint64_t)rows, (uint64_t)K, (uint64_t)ld, 64, 64);
+}
+
+inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+inline int round_up(int a, int b) { return ceil_div(a, b) * b; }
+
+constexpr int kMaxWorld = 32;
+constexpr int kFlagKinds = 3;  // 0: text ready, 1: dtxt slots ready, 2: step done
+
+struct IpcBlob {
+  cudaIpcMemHandle_t txt;
+  cudaIpcMemHandle_t slots;
+  cudaIpcMemHandle_t flags;
+  int rank;
+  int device;
+  int B;
+  int D;
+};
+
+}  // namespace
+
+struct siglip_ctx {
+  int device = 0, rank = 0, world = 1, B = 0, D = 0, Bp = 0;
+  int num_sms = 0;
+  int cta_group = 2;
+  int overlap_pull = 1;
+  __nv_bfloat16* txt_all = nullptr;  // [world][B, D]; slot `rank` is what the peers pull
+  __nv_bfloat16* G = nullptr;        // [Bp, Bp] sigma operand of the current chunk
+  float* g_diag = nullptr;           // [B]
+  float* slots = nullptr;            // [world][B, D] fp32 dtxt contributions, slot c is for owner c (world > 1)
+  double* partials = nullptr;        // [num_sms][4]
+  unsigned int* flags = nullptr;     // [kFlagKinds][kMaxWorld]
+  float* scalars = nullptr;          // [8] device scalars for the host API / debug
+  // peers (index = rank); own entries point at local memory
+  __nv_bfloat16* peer_txt[kMaxWorld] = {};
+  float* peer_slots[kMaxWorld] = {};
+  unsigned int* peer_flags[kMaxWorld] = {};
+  bool peers_ready = false;
+  const float** reduce_ptrs_dev = nullptr;   // [world] device array: peer_slots[p] + rank*B*D
+  unsigned int** signal_ptrs_dev = nullptr;  // [kFlagKinds][world] device array
+  unsigned int step = 0;
+  DebugRecord* dbg_host = nullptr;
+  DebugRecord* dbg_dev = nullptr;
+  unsigned long long launches = 0;
+  size_t workspace_bytes = 0;
+  // host-API staging
+  __nv_bfloat16* h_img = nullptr;
+  __nv_bfloat16* h_txt = nullptr;
+  float* h_dimg = nullptr;
+  float* h_dtxt = nullptr;
+};
+
+namespace {
+
+int check_dbg(siglip_ctx* c, const char* where) {
+  if (c->dbg_host != nullptr && c->dbg_host->code != 0) {
+    char buf[256];
+    snprintf(buf, sizeof(buf), "%s: device wait timed out at site %u (block %u thread %u aux %u %u %u)", where,
+             c->dbg_host->code, c->dbg_host->block, c->dbg_host->thread, c->dbg_host->aux0, c->dbg_host->aux1,
+             c->dbg_host->aux2);
+    return fail(SIGLIP_ERR_CUDA, buf);
+  }
+  return 0;
+}
+
+// The loss kernel over one text chunk: S = img @ txt_c^T on tcgen05, fused scale/bias/log-sigmoid/reduce.
+int run_loss_chunk(siglip_ctx* c, const void* img, const __nv_bfloat16* txt_c, const float* t_prime,
+                   const float* bias, bool own, bool store_g, bool accumulate, const void* pull_src, void* pull_dst,
+                   size_t pull_bytes, const unsigned int* pull_flag, unsigned int pull_value, cudaStream_t st) {
+  const int cg = c->cta_group;
+  const int tile_m = 128 * cg;
+  CUtensorMap tmA, tmB;
+  int rc;
+  if ((rc = encode_operand(&tmA, img, c->B, c->D, c->D, 0, 128))) return rc;
+  if ((rc = encode_operand(&tmB, txt_c, c->B, c->D, c->D, 0, 256 / cg))) return rc;
+  KernelParams p;
+  memset(&p, 0, sizeof(p));
+  p.nprob = 1;
+  p.prob[0].M = c->B;
+  p.prob[0].N = c->B;
+  p.prob[0].K = c->D;
+  p.prob[0].tiles_m = ceil_div(c->B, tile_m);
+  p.prob[0].tiles_n = ceil_div(c->B, 256);
+  p.t_prime = t_prime;
+  p.bias = bias;
+  p.inv_b = 1.0f / static_cast<float>(c->B);
+  p.G = c->G;
+  p.ldg = c->Bp;
+  p.g_diag = c->g_diag;
+  p.own_chunk = own ? 1 : 0;
+  p.store_g = store_g ? 1 : 0;
+  p.partials = c->partials;
+  p.accumulate_partials = accumulate ? 1 : 0;
+  p.dbg = c->dbg_dev;
+  p.pull_src = reinterpret_cast<const uint4*>(pull_src);
+  p.pull_dst = reinterpret_cast<uint4*>(pull_dst);
+  p.pull_bytes = pull_bytes;
+  p.pull_wait_flag = pull_flag;
+  p.pull_wait_value = pull_value;
+  CKI(siglip::launch_gemm(cg, siglip::kModeLoss, &tmA, &tmB, &tmA, &tmB, p, c->num_sms, st));
+  c->launches++;
+  return 0;
+}
+
+// The two gradient contractions of one chunk in one launch:
+//   prob 0: dimg (+)= (t/B) * (G @ txt_c  [+ g_diag * txt_own])      A = G K-major,  B = txt_c N-major
+//   prob 1: dtxt_c  = (t/B) * (G^T @ img  [+ g_diag * img])          A = G M-major,  B = img N-major
+int run_grad_chunk(siglip_ctx* c, const void* img, const __nv_bfloat16* txt_c, const float* t_prime, bool own,
+                   bool beta_dimg, float* dimg, float* dtxt_out, cudaStream_t st) {
+  const int cg = c->cta_group;
+  const int tile_m = 128 * cg;
+  CUtensorMap tmA0, tmB0, tmA1, tmB1;
+  int rc;
+  if ((rc = encode_operand(&tmA0, c->G, c->B, c->B, c->Bp, 0, 128))) return rc;
+  if ((rc = encode_operand(&tmB0, txt_c, c->D, c->B, c->D, 1, 0))) return rc;
+  if ((rc = encode_operand(&tmA1, c->G, c->B, c->B, c->Bp, 1, 0))) return rc;
+  if ((rc = encode_operand(&tmB1, img, c->D, c->B, c->D, 1, 0))) return rc;
+  KernelParams p;
+  memset(&p, 0, sizeof(p));
+  p.nprob = 2;
+  for (int i = 0; i < 2; ++i) {
+    Problem& pr = p.prob[i];
+    pr.M = c->B;
+    pr.N = c->D;
+    pr.K = c->B;
+    pr.tiles_m = ceil_div(c->B, tile_m);
+    pr.tiles_n = ceil_div(c->D, 256);
+    pr.b_mn = 1;
+    pr.ldo = c->D;
+    pr.ldx = c->D;
+    pr.fix_vec = own ? c->g_diag : nullptr;
+  }
+  p.prob[0].a_mn = 0;
+  p.prob[0].out = dimg;
+  p.prob[0].beta = beta_dimg ? 1 : 0;
+  p.prob[0].fix_mat = own ? txt_c : nullptr;
+  p.prob[1].a_mn = 1;
+  p.prob[1].out = dtxt_out;
+  p.prob[1].beta = 0;
+  p.prob[1].fix_mat = own ? reinterpret_cast<const __nv_bfloat16*>(img) : nullptr;
+  p.t_prime = t_prime;
+  p.inv_b = 1.0f / static_cast<float>(c->B);
+  p.dbg = c->dbg_dev;
+  CKI(siglip::launch_gemm(cg, siglip::kModeOut, &tmA0, &tmB0, &tmA1, &tmB1, p, c->num_sms, st));
+  c->launches++;
+  return 0;
+}
+
+int signal_peers(siglip_ctx* c, int kind, unsigned int value, cudaStream_t st) {
+  CKI(siglip::launch_signal_flags(c->signal_ptrs_dev + kind * c->world, c->world, value, st));
+  c->launches++;
+  return 0;
+}
+
+int wait_peers(siglip_ctx* c, int kind, unsigned int value, cudaStream_t st) {
+  CKI(siglip::launch_wait_flags(c->flags + kind * kMaxWorld, c->world, value, c->dbg_dev, st));
+  c->launches++;
+  return 0;
+}
+
+int step_impl(siglip_ctx* c, const void* img, const void* txt, const float* t_prime, const float* bias, float* loss,
+              float* dimg, float* dtxt, float* dt_prime, float* dbias, bool with_grad, cudaStream_t st) {
+  if (c == nullptr || img == nullptr || txt == nullptr || t_prime == nullptr || bias == nullptr || loss == nullptr)
+    return fail(SIGLIP_ERR_INVALID, "null argument");
+  if (with_grad && (dimg == nullptr || dtxt == nullptr || dt_prime == nullptr || dbias == nullptr))
+    return fail(SIGLIP_ERR_INVALID, "null gradient pointer");
+  if (c->world > 1 && !c->peers_ready)
+    return fail(SIGLIP_ERR_STATE, "world > 1 but peer handles were not imported (siglip_ctx_import_handles)");
+  int rc;
+  if ((rc = check_dbg(c, "siglip step (previous launch)"))) return rc;
+  CK(cudaSetDevice(c->device));
+  const int W = c->world, r = c->rank;
+  const size_t chunk_elems = static_cast<size_t>(c->B) * c->D;
+  const size_t chunk_bytes = chunk_elems * sizeof(__nv_bfloat16);
+  c->step++;
+  const unsigned int s = c->step;
+
+  const __nv_bfloat16* own_txt = reinterpret_cast<const __nv_bfloat16*>(txt);
+  if (W > 1) {
+    // peers must have finished reading my text slot / dtxt slots of the previous step before I overwrite them
+    if ((rc = wait_peers(c, 2, s - 1, st))) return rc;
+    CK(cudaMemcpyAsync(c->txt_all + r * chunk_elems, txt, chunk_bytes, cudaMemcpyDeviceToDevice, st));
+    c->launches++;
+    if ((rc = signal_peers(c, 0, s, st))) return rc;
+    own_txt = c->txt_all + r * chunk_elems;
+  }
+
+  CKI(siglip::launch_zero_partials(c->partials, c->num_sms, st));
+  c->launches++;
+
+  // Chunk schedule: step k scores my images against the text chunk owned by rank (r + k) % W — the order in
+  // which the reference's ring delivers them (rwightman_sigmoid_loss.py:108-122), without the hop-by-hop
+  // forwarding: every chunk is pulled straight from its owner through the NVSwitch.
+  for (int k = 0; k < W; ++k) {
+    const int cidx = (r + k) % W;
+    const __nv_bfloat16* txt_c = (k == 0) ? own_txt : c->txt_all + cidx * chunk_elems;
+    const void* pull_src = nullptr;
+    void* pull_dst = nullptr;
+    size_t pull_bytes = 0;
+    const unsigned int* pull_flag = nullptr;
+    if (k + 1 < W) {
+      const int nxt = (r + k + 1) % W;
+      pull_src = c->peer_txt[nxt] + nxt * chunk_elems;
+      pull_dst = c->txt_all + nxt * chunk_elems;
+      pull_bytes = chunk_bytes;
+      pull_flag = c->flags + 0 * kMaxWorld + nxt;
+    }
+    if (!c->overlap_pull && pull_bytes != 0) {
+      // un-overlapped variant (for A/B measurements): wait + copy as separate stream operations
+      if ((rc = wait_peers(c, 0, s, st))) return rc;
+      CK(cudaMemcpyAsync(pull_dst, pull_src, pull_bytes, cudaMemcpyDefault, st));
+      c->launches++;
+      pull_bytes = 0;
+      pull_src = pull_dst = nullptr;
+      pull_flag = nullptr;
+    }
+    if ((rc = run_loss_chunk(c, img, txt_c, t_prime, bias, k == 0, with_grad, true, pull_src, pull_dst, pull_bytes,
+                             pull_flag, s, st)))
+      return rc;
+    if (with_grad) {
+      float* dtxt_out = (W == 1) ? dtxt : c->slots + cidx * chunk_elems;
+      if ((rc = run_grad_chunk(c, img, txt_c, t_prime, k == 0, k > 0, dimg, dtxt_out, st))) return rc;
+    }
+  }
+  CKI(siglip::launch_finalize(c->partials, c->num_sms, t_prime, 1.0f / static_cast<float>(c->B), loss,
+                              with_grad ? dt_prime : nullptr, with_grad ? dbias : nullptr, st));
+  c->launches++;
+
+  if (W > 1) {
+    if (with_grad) {
+      // dtxt of my text rows = sum over ranks of their contribution slot for me: what all_gather's backward
+      // (reduce-scatter SUM, torch functional.py:343-354) or the reverse ring (distributed_utils.py:75-77) delivers.
+      if ((rc = signal_peers(c, 1, s, st))) return rc;
+      if ((rc = wait_peers(c, 1, s, st))) return rc;
+      CKI(siglip::launch_reduce_slots(dtxt, c->reduce_ptrs_dev, W, chunk_elems, c->num_sms, st));
+      c->launches++;
+    }
+    if ((rc = signal_peers(c, 2, s, st))) return rc;
+  }
+  CK(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* siglip_version(void) { return "siglip_b200 0.1.0 sm_100a"; }
+
+const char* siglip_last_error(void) { return g_last_error.c_str(); }
+
+int siglip_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  int ok = 0;
+  for (int i = 0; i < n; ++i) {
+    int major = 0;
+    if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, i) == cudaSuccess && major == 10) ok++;
+  }
+  return ok;
+}
+
+int siglip_ctx_create(siglip_ctx** out, int device, int rank, int world, int B, int D) {
+  if (out == nullptr) return fail(SIGLIP_ERR_INVALID, "out is null");
+  *out = nullptr;
+  if (world < 1 || world > kMaxWorld || rank < 0 || rank >= world)
+    return fail(SIGLIP_ERR_INVALID, "rank/world out of range (world <= 32)");
+  if (B < 1 || D < 8 || (D % 8) != 0) return fail(SIGLIP_ERR_INVALID, "need B >= 1 and D a positive multiple of 8");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    cudaGetLastError();
+    return fail(SIGLIP_ERR_NO_DEVICE, "no CUDA device visible; this library has no CPU fallback");
+  }
+  if (device < 0 || device >= ndev) return fail(SIGLIP_ERR_INVALID, "device ordinal out of range");
+  int major = 0;
+  CK(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, device));
+  if (major != 10) return fail(SIGLIP_ERR_NO_DEVICE, "device is not compute capability 10.x (B200, sm_100a required)");
+  CK(cudaSetDevice(device));
+  siglip_ctx* c = new siglip_ctx();
+  c->device = device;
+  c->rank = rank;
+  c->world = world;
+  c->B = B;
+  c->D = D;
+  c->Bp = round_up(B, 256);
+  CK(cudaDeviceGetAttribute(&c->num_sms, cudaDevAttrMultiProcessorCount, device));
+  const size_t chunk_elems = static_cast<size_t>(B) * D;
+  size_t total = 0;
+  auto alloc = [&](void** p, size_t bytes) -> cudaError_t {
+    total += bytes;
+    return cudaMalloc(p, bytes);
+  };
+  CK(alloc(reinterpret_cast<void**>(&c->G), static_cast<size_t>(c->Bp) * c->Bp * sizeof(__nv_bfloat16)));
+  CK(alloc(reinterpret_cast<void**>(&c->g_diag), static_cast<size_t>(c->Bp) * sizeof(float)));
+  CK(alloc(reinterpret_cast<void**>(&c->partials), static_cast<size_t>(c->num_sms) * 4 * sizeof(double)));
+  CK(alloc(reinterpret_cast<void**>(&c->flags), kFlagKinds * kMaxWorld * sizeof(unsigned int)));
+  CK(alloc(reinterpret_cast<void**>(&c->scalars), 8 * sizeof(float)));
+  CK(cudaMemset(c->flags, 0, kFlagKinds * kMaxWorld * sizeof(unsigned int)));
+  CK(cudaMemset(c->partials, 0, static_cast<size_t>(c->num_sms) * 4 * sizeof(double)));
+  CK(cudaMemset(c->g_diag, 0, static_cast<size_t>(c->Bp) * sizeof(float)));
+  CK(cudaMemset(c->scalars, 0, 8 * sizeof(float)));
+  if (world > 1) {
+    CK(alloc(reinterpret_cast<void**>(&c->txt_all), chunk_elems * world * sizeof(__nv_bfloat16)));
+    CK(alloc(reinterpret_cast<void**>(&c->slots), chunk_elems * world * sizeof(float)));
+    CK(alloc(reinterpret_cast<void**>(&c->reduce_ptrs_dev), world * sizeof(float*)));
+    CK(alloc(reinterpret_cast<void**>(&c->signal_ptrs_dev), kFlagKinds * world * sizeof(unsigned int*)));
+  }
+  CK(cudaHostAlloc(reinterpret_cast<void**>(&c->dbg_host), sizeof(DebugRecord), cudaHostAllocMapped));
+  memset(c->dbg_host, 0, sizeof(DebugRecord));
+  CK(cudaHostGetDevicePointer(reinterpret_cast<void**>(&c->dbg_dev), c->dbg_host, 0));
+  c->peer_txt[rank] = c->txt_all;
+  c->peer_slots[rank] = c->slots;
+  c->peer_flags[rank] = c->flags;
+  c->workspace_bytes = total;
+  CK(cudaDeviceSynchronize());
+  *out = c;
+  return 0;
+}
+
+int siglip_ctx_set_option(siglip_ctx* c, int option, int value) {
+  if (c == nullptr) return fail(SIGLIP_ERR_INVALID, "ctx is null");
+  switch (option) {
+    case SIGLIP_OPT_CTA_GROUP:
+      if (value != 1 && value != 2) return fail(SIGLIP_ERR_INVALID, "cta_group must be 1 or 2");
+      c->cta_group = value;
+      return 0;
+    case SIGLIP_OPT_OVERLAP_PULL:
+      c->overlap_pull = value ? 1 : 0;
+      return 0;
+    default:
+      return fail(SIGLIP_ERR_INVALID, "unknown option");
+  }
+}
+
+size_t siglip_ctx_workspace_bytes(const siglip_ctx* c) { return c ? c->workspace_bytes : 0; }
+
+size_t siglip_ctx_handle_bytes(void) { return sizeof(IpcBlob); }
+
+int siglip_ctx_export_handles(siglip_ctx* c, void* out_bytes, size_t capacity) {
+  if (c == nullptr || out_bytes == nullptr) return fail(SIGLIP_ERR_INVALID, "null argument");
+  if (capacity < sizeof(IpcBlob)) return fail(SIGLIP_ERR_INVALID, "handle buffer too small");
+  if (c->world == 1) return fail(SIGLIP_ERR_STATE, "world == 1 has no peers to export to");
+  CK(cudaSetDevice(c->device));
+  IpcBlob b;
+  memset(&b, 0, sizeof(b));
+  CK(cudaIpcGetMemHandle(&b.txt, c->txt_all));
+  CK(cudaIpcGetMemHandle(&b.slots, c->slots));
+  CK(cudaIpcGetMemHandle(&b.flags, c->flags));
+  b.rank = c->rank;
+  b.device = c->device;
+  b.B = c->B;
+  b.D = c->D;
+  memcpy(out_bytes, &b, sizeof(b));
+  return 0;
+}
+
+int siglip_ctx_import_handles(siglip_ctx* c, const void* all_ranks_bytes, size_t bytes_per_rank) {
+  if (c == nullptr || all_ranks_bytes == nullptr) return fail(SIGLIP_ERR_INVALID, "null argument");
+  if (bytes_per_rank != sizeof(IpcBlob)) return fail(SIGLIP_ERR_INVALID, "bytes_per_rank != siglip_ctx_handle_bytes()");
+  if (c->world == 1) return fail(SIGLIP_ERR_STATE, "world == 1 has no peers to import");
+  CK(cudaSetDevice(c->device));
+  const char* base = static_cast<const char*>(all_ranks_bytes);
+  for (int p = 0; p < c->world; ++p) {
+    IpcBlob b;
+    memcpy(&b, base + static_cast<size_t>(p) * bytes_per_rank, sizeof(b));
+    if (b.rank != p) return fail(SIGLIP_ERR_INVALID, "handle blobs are not ordered by rank");
+    if (b.B != c->B || b.D != c->D)
+      return fail(SIGLIP_ERR_INVALID, "peer context has a different (B, D): every rank must use the same batch");
+    if (p == c->rank) continue;
+    void *pt = nullptr, *ps = nullptr, *pf = nullptr;
+    CK(cudaIpcOpenMemHandle(&pt, b.txt, cudaIpcMemLazyEnablePeerAccess));
+    CK(cudaIpcOpenMemHandle(&ps, b.slots, cudaIpcMemLazyEnablePeerAccess));
+    CK(cudaIpcOpenMemHandle(&pf, b.flags, cudaIpcMemLazyEnablePeerAccess));
+    c->peer_txt[p] = static_cast<__nv_bfloat16*>(pt);
+    c->peer_slots[p] = static_cast<float*>(ps);
+    c->peer_flags[p] = static_cast<unsigned int*>(pf);
+  }
+  const size_t chunk_elems = static_cast<size_t>(c->B) * c->D;
+  std::vector<const float*> red(c->world);
+  for (int p = 0; p < c->world; ++p) red[p] = c->peer_slots[p] + c->rank * chunk_elems;
+  CK(cudaMemcpy(c->reduce_ptrs_dev, red.data(), c->world * sizeof(float*), cudaMemcpyHostToDevice));
+  std::vector<unsigned int*> sig(kFlagKinds * c->world);
+  for (int k = 0; k < kFlagKinds; ++k)
+    for (int p = 0; p < c->world; ++p) sig[k * c->world + p] = c->peer_flags[p] + k * kMaxWorld + c->rank;
+  CK(cudaMemcpy(c->signal_ptrs_dev, sig.data(), sig.size() * sizeof(unsigned int*), cudaMemcpyHostToDevice));
+  c->peers_ready = true;
+  return 0;
+}
+
+int siglip_fwd_bwd(siglip_ctx* c, const void* img, const void* txt, const float* t_prime, const float* bias,
+                   float* loss, float* dimg, float* dtxt, float* dt_prime, float* dbias, void* cuda_stream) {
+  return step_impl(c, img, txt, t_prime, bias, loss, dimg, dtxt, dt_prime, dbias, true,
+                   static_cast<cudaStream_t>(cuda_stream));
+}
+
+int siglip_fwd(siglip_ctx* c, const void* img, const void* txt, const float* t_prime, const float* bias, float* loss,
+               void* cuda_stream) {
+  return step_impl(c, img, txt, t_prime, bias, loss, nullptr, nullptr, nullptr, nullptr, false,
+                   static_cast<cudaStream_t>(cuda_stream));
+}
+
+int siglip_fwd_bwd_host(siglip_ctx* c, const void* img_host, const void* txt_host, float t_prime, float bias,
+                        float* loss_host, float* dimg_host, float* dtxt_host, float* dt_prime_host,
+                        float* dbias_host, void* cuda_stream) {
+  if (c == nullptr || img_host == nullptr || txt_host == nullptr || loss_host == nullptr)
+    return fail(SIGLIP_ERR_INVALID, "null argument");
+  cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+  CK(cudaSetDevice(c->device));
+  const size_t chunk_elems = static_cast<size_t>(c->B) * c->D;
+  if (c->h_img == nullptr) {
+    CK(cudaMalloc(reinterpret_cast<void**>(&c->h_img), chunk_elems * sizeof(__nv_bfloat16)));
+    CK(cudaMalloc(reinterpret_cast<void**>(&c->h_txt), chunk_elems * sizeof(__nv_bfloat16)));
+    CK(cudaMalloc(reinterpret_cast<void**>(&c->h_dimg), chunk_elems * sizeof(float)));
+    CK(cudaMalloc(reinterpret_cast<void**>(&c->h_dtxt), chunk_elems * sizeof(float)));
+    c->workspace_bytes += chunk_elems * (2 * sizeof(__nv_bfloat16) + 2 * sizeof(float));
+  }
+  const float sc[2] = {t_prime, bias};
+  CK(cudaMemcpyAsync(c->scalars, sc, sizeof(sc), cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(c->h_img, img_host, chunk_elems * sizeof(__nv_bfloat16), cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(c->h_txt, txt_host, chunk_elems * sizeof(__nv_bfloat16), cudaMemcpyHostToDevice, st));
+  int rc = step_impl(c, c->h_img, c->h_txt, c->scalars + 0, c->scalars + 1, c->scalars + 2, c->h_dimg, c->h_dtxt,
+                     c->scalars + 3, c->scalars + 4, true, st);
+  if (rc) return rc;
+  float res[3];
+  CK(cudaMemcpyAsync(res, c->scalars + 2, sizeof(res), cudaMemcpyDeviceToHost, st));
+  if (dimg_host) CK(cudaMemcpyAsync(dimg_host, c->h_dimg, chunk_elems * sizeof(float), cudaMemcpyDeviceToHost, st));
+  if (dtxt_host) CK(cudaMemcpyAsync(dtxt_host, c->h_dtxt, chunk_elems * sizeof(float), cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  if ((rc = check_dbg(c, "siglip_fwd_bwd_host"))) return rc;
+  *loss_host = res[0];
+  if (dt_prime_host) *dt_prime_host = res[1];
+  if (dbias_host) *dbias_host = res[2];
+  return 0;
+}
+
+unsigned long long siglip_ctx_launch_count(const siglip_ctx* c) { return c ? c->launches : 0ull; }
+
+int siglip_debug_gemm(int device, int cta_group, int M, int N, int K, const void* A, long long lda, int a_mn,
+                      const void* Bm, long long ldb, int b_mn, float* C, long long ldc, void* cuda_stream) {
+  if (A == nullptr || Bm == nullptr || C == nullptr) return fail(SIGLIP_ERR_INVALID, "null argument");
+  if (cta_group != 1 && cta_group != 2) return fail(SIGLIP_ERR_INVALID, "cta_group must be 1 or 2");
+  if (M < 1 || N < 4 || K < 1 || (N % 4) != 0) return fail(SIGLIP_ERR_INVALID, "need N % 4 == 0");
+  if (siglip_device_count() == 0) return fail(SIGLIP_ERR_NO_DEVICE, "no sm_100 device; no CPU fallback");
+  CK(cudaSetDevice(device));
+  cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+  int num_sms = 0;
+  CK(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, device));
+  CUtensorMap tmA, tmB;
+  int rc;
+  if ((rc = encode_operand(&tmA, A, M, K, lda, a_mn, 128))) return rc;
+  if ((rc = encode_operand(&tmB, Bm, N, K, ldb, b_mn, 256 / cta_group))) return rc;
+  float* zero = nullptr;  // t' = 0 -> scale exp(0) * 1 = 1
+  CK(cudaMalloc(reinterpret_cast<void**>(&zero), sizeof(float)));
+  CK(cudaMemsetAsync(zero, 0, sizeof(float), st));
+  DebugRecord* dbg_host = nullptr;
+  DebugRecord* dbg_dev = nullptr;
+  CK(cudaHostAlloc(reinterpret_cast<void**>(&dbg_host), sizeof(DebugRecord), cudaHostAllocMapped));
+  memset(dbg_host, 0, sizeof(DebugRecord));
+  CK(cudaHostGetDevicePointer(reinterpret_cast<void**>(&dbg_dev), dbg_host, 0));
+  KernelParams p;
+  memset(&p, 0, sizeof(p));
+  p.nprob = 1;
+  p.prob[0].M = M;
+  p.prob[0].N = N;
+  p.prob[0].K = K;
+  p.prob[0].tiles_m = ceil_div(M, 128 * cta_group);
+  p.prob[0].tiles_n = ceil_div(N, 256);
+  p.prob[0].a_mn = a_mn ? 1 : 0;
+  p.prob[0].b_mn = b_mn ? 1 : 0;
+  p.prob[0].out = C;
+  p.prob[0].ldo = ldc;
+  p.t_prime = zero;
+  p.inv_b = 1.0f;
+  p.dbg = dbg_dev;
+  int lrc = siglip::launch_gemm(cta_group, siglip::kModeOut, &tmA, &tmB, &tmA, &tmB, p, num_sms, st);
+  cudaError_t se = cudaStreamSynchronize(st);
+  int result = 0;
+  if (dbg_host->code != 0) {
+    char buf[256];
+    snprintf(buf, sizeof(buf), "debug gemm: device wait timed out at site %u (block %u thread %u aux %u %u %u)",
+             dbg_host->code, dbg_host->block, dbg_host->thread, dbg_host->aux0, dbg_host->aux1, dbg_host->aux2);
+    result = fail(SIGLIP_ERR_CUDA, buf);
+  } else if (lrc != 0) {
+    result = fail(SIGLIP_ERR_CUDA, std::string("debug gemm launch failed: ") +
+                                       cudaGetErrorString(static_cast<cudaError_t>(lrc)));
+  } else if (se != cudaSuccess) {
+    result = fail(SIGLIP_ERR_CUDA, std::string("debug gemm execution failed: ") + cudaGetErrorString(se));
+  }
+  cudaFreeHost(dbg_host);
+  cudaFree(zero);
+  return result;
+}
+
+void siglip_ctx_destroy(siglip_ctx* c) {
+  if (c == nullptr) return;
+  cudaSetDevice(c->device);
+  cudaDeviceSynchronize();
+  for (int p = 0; p < c->world; ++p) {
+    if (p == c->rank) continue;
+    if (c->peer_txt[p]) cudaIpcCloseMemHandle(c->peer_txt[p]);
+    if (c->peer_slots[p]) cudaIpcCloseMemHandle(c->peer_slots[p]);
+    if (c->peer_flags[p]) cudaIpcCloseMemHandle(c->peer_flags[p]);
+  }
+  cudaFree(c->txt_all);
+  cudaFree(c->G);
+  cudaFree(c->g_diag);
+  cudaFree(c->slots);
+  cudaFree(c->partials);
+  cudaFree(c->flags);
+  cudaFree(c->scalars);
+  cudaFree(c->reduce_ptrs_dev);
+  cudaFree(c->signal_ptrs_dev);
+  cudaFree(c->h_img);
+  cudaFree(c->h_txt);
+  cudaFree(c->h_dimg);
+  cudaFree(c->h_dtxt);
+  if (c->dbg_host) cudaFreeHost(c->dbg_host);
+  cudaGetLastError();
+  delete c;
+}
+
+}  // extern "C"

@@ -1,0 +1,79 @@
+// Host-visible declarations of the sm_100a kernels (definitions in siglip_kernels.cu).
+#pragma once
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "ptx.cuh"
+
+namespace siglip {
+
+// One dense contraction C[M,N] = A[M,K] * B[N,K]^T on the tcgen05 pipe.
+// `a_mn` / `b_mn` say how the operand sits in memory:
+//   0: K-major  — global tensor is [rows][K], K contiguous      (TMA box {64 k, rows})
+//   1: MN-major — global tensor is [K][rows], rows contiguous   (TMA boxes {64 rows, 64 k})
+struct Problem {
+  int M, N, K;
+  int tiles_m, tiles_n;
+  int a_mn, b_mn;
+  // epilogue of the "out" kernel: out = (beta ? out : 0) + scale * (acc + fix_vec[row] * fix_mat[row, col])
+  float* out;
+  long long ldo;
+  const float* fix_vec;
+  const __nv_bfloat16* fix_mat;
+  long long ldx;
+  int beta;
+};
+
+struct KernelParams {
+  Problem prob[2];
+  int nprob;
+  // learnable scalars, device memory (reference: distributed_sigmoid_loss.py:11-12)
+  const float* t_prime;
+  const float* bias;
+  float inv_b;  // 1 / per-rank batch (reference divides by the LOCAL batch, distributed_sigmoid_loss.py:47)
+  // epilogue of the "loss" kernel
+  __nv_bfloat16* G;  // [Bp, ldg] bf16 sigma terms, diagonal zeroed; may be null when store_g == 0
+  long long ldg;
+  float* g_diag;   // [B] fp32: -sigma(-z_ii), the positive-pair term kept out of the bf16 operand
+  int own_chunk;   // 1: this text chunk holds the positives of this rank's images
+  int store_g;     // 0: forward only
+  double* partials;  // [gridDim.x][4] : sum softplus, sum g, sum g*s, (unused)
+  int accumulate_partials;
+  DebugRecord* dbg;
+  // optional NVSwitch peer pull performed by otherwise idle warps while the tiles compute:
+  // copy `pull_bytes` from pull_src (peer GPU memory, P2P mapped) to pull_dst (local), both 16-B aligned.
+  const uint4* pull_src;
+  uint4* pull_dst;
+  unsigned long long pull_bytes;
+  // flag the pull must see (>= pull_wait_value) before reading the peer buffer; null = no wait
+  const volatile unsigned int* pull_wait_flag;
+  unsigned int pull_wait_value;
+};
+
+enum KernelMode { kModeLoss = 0, kModeOut = 1 };
+
+// Dynamic shared memory needed by a configuration.
+size_t gemm_smem_bytes(int cta_group);
+
+// Launch the warp-specialised persistent kernel. Returns cudaError_t as int.
+int launch_gemm(int cta_group, int mode, const CUtensorMap* tmA0, const CUtensorMap* tmB0, const CUtensorMap* tmA1,
+                const CUtensorMap* tmB1, const KernelParams& p, int num_sms, cudaStream_t stream);
+
+// loss = inv_b * S0 ; dbias = inv_b * S1 ; dt_prime = exp(t') * inv_b * S2  (S* = fixed-order sums of partials)
+int launch_finalize(const double* partials, int nparts, const float* t_prime, float inv_b, float* loss,
+                    float* dt_prime, float* dbias, cudaStream_t stream);
+
+int launch_zero_partials(double* partials, int nparts, cudaStream_t stream);
+
+// dtxt[j, d] = sum_r slots[r][j, d]   (slots may be peer-mapped pointers; fp32; n = elements)
+int launch_reduce_slots(float* out, const float* const* slots_dev, int nslots, size_t n, int num_sms,
+                        cudaStream_t stream);
+
+// cross-rank flag helpers (peer-mapped pointers)
+int launch_signal_flags(unsigned int* const* flag_ptrs_dev, int n, unsigned int value, cudaStream_t stream);
+int launch_wait_flags(const volatile unsigned int* flags, int n, unsigned int value, DebugRecord* dbg,
+                      cudaStream_t stream);
+
+}  // namespace siglip

@@ -1,0 +1,264 @@
+"""Host-side mirror of the reference's module surface over the sm_100a C-ABI library.
+
+Reference interface (ahmdtaha/distributed_sigmoid_loss):
+  * ``DDPSigmoidLoss(gpu_batch_size).forward(image_embeddings, text_embeddings)``
+    (distributed_sigmoid_loss.py:8-48) with learnable ``t_prime`` / ``bias`` (:11-12),
+  * ``SigLipLoss(cache_labels, rank, world_size, bidir, use_horovod).forward(image_features,
+    text_features, logit_scale, logit_bias, output_dict=False)`` (rwightman_sigmoid_loss.py:23-30, 68).
+
+Same names, same argument meaning, same error behaviour (``RuntimeError`` when the batch does not match
+``gpu_batch_size``). The arithmetic runs in ``libsiglip_b200.so`` only: PyTorch supplies device memory,
+the stream and the process group used to exchange CUDA-IPC handles once. No CPU path exists here.
+"""
+from __future__ import annotations
+
+import ctypes
+import math
+from typing import Dict, Optional, Tuple
+
+import torch
+import torch.distributed as dist
+import torch.nn as nn
+
+from . import _capi
+
+
+def _group_rank_world(group) -> Tuple[int, int]:
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_rank(group), dist.get_world_size(group)
+    return 0, 1
+
+
+def chunk_schedule(rank: int, world: int):
+    """Order in which a rank scores its images against the text chunks: own chunk first, then the chunks of
+    ranks rank+1, rank+2, ... (mod world). Same visiting order as the reference's unidirectional ring
+    (rwightman_sigmoid_loss.py:108-122 receives from the left neighbour, i.e. rank-1, rank-2, ...; the set of
+    (image-rank, text-chunk) pairs covered is identical, only the direction differs)."""
+    return [(rank + k) % world for k in range(world)]
+
+
+class SigmoidLossEngine:
+    """Owns one ``siglip_ctx`` (workspaces + peer mappings) for a fixed (device, B, D, process group)."""
+
+    def __init__(self, batch: int, dim: int, device: torch.device, group=None, cta_group: int = 2,
+                 overlap_pull: bool = True):
+        self._L = _capi.lib()
+        if not torch.cuda.is_available() or self._L.siglip_device_count() == 0:
+            raise RuntimeError("distributed_sigmoid_loss_b200 needs an sm_100 (B200) device; there is no CPU fallback")
+        self.batch, self.dim, self.device, self.group = batch, dim, torch.device(device), group
+        self.rank, self.world = _group_rank_world(group)
+        h = ctypes.c_void_p()
+        _capi.check(self._L.siglip_ctx_create(ctypes.byref(h), self.device.index or 0, self.rank, self.world,
+                                              batch, dim))
+        self._h = h
+        _capi.check(self._L.siglip_ctx_set_option(h, _capi.SIGLIP_OPT_CTA_GROUP, int(cta_group)))
+        _capi.check(self._L.siglip_ctx_set_option(h, _capi.SIGLIP_OPT_OVERLAP_PULL, int(bool(overlap_pull))))
+        if self.world > 1:
+            self._exchange_handles()
+
+    # -- peer bootstrap: replaces the reference's reliance on the process group for every step ------------
+    def _exchange_handles(self) -> None:
+        n = int(self._L.siglip_ctx_handle_bytes())
+        buf = ctypes.create_string_buffer(n)
+        _capi.check(self._L.siglip_ctx_export_handles(self._h, buf, n))
+        blobs = [None] * self.world
+        dist.all_gather_object(blobs, bytes(buf.raw), group=self.group)
+        joined = b"".join(blobs)
+        _capi.check(self._L.siglip_ctx_import_handles(self._h, joined, n))
+        dist.barrier(group=self.group)
+
+    def set_option(self, option: int, value: int) -> None:
+        _capi.check(self._L.siglip_ctx_set_option(self._h, option, value))
+
+    @property
+    def workspace_bytes(self) -> int:
+        return int(self._L.siglip_ctx_workspace_bytes(self._h))
+
+    @property
+    def launch_count(self) -> int:
+        return int(self._L.siglip_ctx_launch_count(self._h))
+
+    def _stream(self) -> int:
+        return torch.cuda.current_stream(self.device).cuda_stream
+
+    def fwd_bwd(self, img: torch.Tensor, txt: torch.Tensor, t_prime: torch.Tensor, bias: torch.Tensor):
+        """img/txt: [B, D] bf16 contiguous on self.device; t_prime/bias: fp32 [1]. Returns fp32 tensors
+        (loss[1], dimg[B,D], dtxt[B,D], dt_prime[1], dbias[1]) for an upstream gradient of 1."""
+        self._check(img, txt)
+        opts = dict(device=self.device, dtype=torch.float32)
+        loss = torch.empty(1, **opts)
+        dimg = torch.empty(self.batch, self.dim, **opts)
+        dtxt = torch.empty(self.batch, self.dim, **opts)
+        dtp = torch.empty(1, **opts)
+        db = torch.empty(1, **opts)
+        with torch.cuda.device(self.device):
+            _capi.check(self._L.siglip_fwd_bwd(self._h, img.data_ptr(), txt.data_ptr(), t_prime.data_ptr(),
+                                               bias.data_ptr(), loss.data_ptr(), dimg.data_ptr(), dtxt.data_ptr(),
+                                               dtp.data_ptr(), db.data_ptr(), self._stream()))
+        return loss, dimg, dtxt, dtp, db
+
+    def fwd(self, img: torch.Tensor, txt: torch.Tensor, t_prime: torch.Tensor, bias: torch.Tensor) -> torch.Tensor:
+        self._check(img, txt)
+        loss = torch.empty(1, device=self.device, dtype=torch.float32)
+        with torch.cuda.device(self.device):
+            _capi.check(self._L.siglip_fwd(self._h, img.data_ptr(), txt.data_ptr(), t_prime.data_ptr(),
+                                           bias.data_ptr(), loss.data_ptr(), self._stream()))
+        return loss
+
+    def fwd_bwd_host(self, img_host: torch.Tensor, txt_host: torch.Tensor, t_prime: float, bias: float,
+                     dimg_host: Optional[torch.Tensor] = None, dtxt_host: Optional[torch.Tensor] = None):
+        """End-to-end step on HOST bf16 buffers (pinned recommended): H2D, step, D2H inside one C call.
+        Returns (loss, dt_prime, dbias) as Python floats."""
+        for x in (img_host, txt_host):
+            if x.device.type != "cpu" or x.dtype != torch.bfloat16 or not x.is_contiguous() or \
+                    tuple(x.shape) != (self.batch, self.dim):
+                raise RuntimeError("fwd_bwd_host expects contiguous CPU bf16 tensors of shape [B, D]")
+        out = (ctypes.c_float * 3)()
+        loss_p = ctypes.cast(out, ctypes.c_void_p).value
+        with torch.cuda.device(self.device):
+            _capi.check(self._L.siglip_fwd_bwd_host(
+                self._h, img_host.data_ptr(), txt_host.data_ptr(), float(t_prime), float(bias), loss_p,
+                dimg_host.data_ptr() if dimg_host is not None else None,
+                dtxt_host.data_ptr() if dtxt_host is not None else None,
+                loss_p + 4, loss_p + 8, self._stream()))
+        return float(out[0]), float(out[1]), float(out[2])
+
+    def _check(self, img: torch.Tensor, txt: torch.Tensor) -> None:
+        for x in (img, txt):
+            if x.device != self.device or x.dtype != torch.bfloat16 or not x.is_contiguous() or \
+                    tuple(x.shape) != (self.batch, self.dim):
+                raise RuntimeError(
+                    f"engine expects contiguous bf16 [{self.batch}, {self.dim}] tensors on {self.device}, got "
+                    f"{tuple(x.shape)} {x.dtype} on {x.device}")
+
+    def close(self) -> None:
+        if getattr(self, "_h", None) is not None and self._h.value:
+            self._L.siglip_ctx_destroy(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __del__(self):  # best effort
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class _SigmoidLossFn(torch.autograd.Function):
+    """loss = sum_chunks(-logsigmoid(labels * (img @ txt_chunk.T * exp(t') + b))).sum() / B, with the four
+    gradients produced in the same fused pass: backward only scales by the upstream scalar."""
+
+    @staticmethod
+    def forward(ctx, img, txt, t_prime, bias, engine: SigmoidLossEngine):
+        need_grad = any(ctx.needs_input_grad[:4])
+        img_b = img.detach().to(torch.bfloat16).contiguous()
+        txt_b = txt.detach().to(torch.bfloat16).contiguous()
+        tp = t_prime.detach().to(device=img.device, dtype=torch.float32).reshape(1)
+        b = bias.detach().to(device=img.device, dtype=torch.float32).reshape(1)
+        ctx.in_meta = (img.dtype, txt.dtype, t_prime.dtype, bias.dtype, t_prime.shape, bias.shape,
+                       t_prime.device, bias.device)
+        if need_grad:
+            loss, dimg, dtxt, dtp, db = engine.fwd_bwd(img_b, txt_b, tp, b)
+            ctx.save_for_backward(dimg, dtxt, dtp, db)
+        else:
+            loss = engine.fwd(img_b, txt_b, tp, b)
+        # reference result dtype: promote(input dtype, fp32 labels) (distributed_sigmoid_loss.py:28-32)
+        out_dtype = torch.promote_types(img.dtype, torch.float32)
+        return loss.reshape(()).to(out_dtype)
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        dimg, dtxt, dtp, db = ctx.saved_tensors
+        idt, tdt, pdt, bdt, pshape, bshape, pdev, bdev = ctx.in_meta
+        g = grad_out.to(torch.float32)
+        gi = (dimg * g).to(idt) if ctx.needs_input_grad[0] else None
+        gt = (dtxt * g).to(tdt) if ctx.needs_input_grad[1] else None
+        gp = (dtp * g).reshape(pshape).to(device=pdev, dtype=pdt) if ctx.needs_input_grad[2] else None
+        gb = (db * g).reshape(bshape).to(device=bdev, dtype=bdt) if ctx.needs_input_grad[3] else None
+        return gi, gt, gp, gb, None
+
+
+class _EngineCache:
+    def __init__(self, group=None, cta_group: int = 2, overlap_pull: bool = True):
+        self.group, self.cta_group, self.overlap_pull = group, cta_group, overlap_pull
+        self._engines: Dict[Tuple[int, int, int], SigmoidLossEngine] = {}
+
+    def get(self, batch: int, dim: int, device: torch.device) -> SigmoidLossEngine:
+        key = (device.index if device.index is not None else torch.cuda.current_device(), batch, dim)
+        eng = self._engines.get(key)
+        if eng is None:
+            dev = torch.device("cuda", key[0])
+            eng = SigmoidLossEngine(batch, dim, dev, self.group, self.cta_group, self.overlap_pull)
+            self._engines[key] = eng
+        return eng
+
+
+def _validate(image_embeddings: torch.Tensor, text_embeddings: torch.Tensor, expect_batch: Optional[int]) -> None:
+    if image_embeddings.dim() != 2 or text_embeddings.dim() != 2:
+        raise RuntimeError("image_embeddings and text_embeddings must be 2-D [batch, emb_dim]")
+    if image_embeddings.shape != text_embeddings.shape:
+        raise RuntimeError(
+            f"image_embeddings {tuple(image_embeddings.shape)} and text_embeddings {tuple(text_embeddings.shape)} "
+            "must have the same shape (local batch on every rank)")
+    if expect_batch is not None and image_embeddings.shape[0] != expect_batch:
+        # the reference fails with a broadcast RuntimeError when B != gpu_batch_size
+        raise RuntimeError(
+            f"The size of tensor a ({image_embeddings.shape[0]}) must match the size of tensor b ({expect_batch}): "
+            "batch does not equal gpu_batch_size")
+    if image_embeddings.device.type != "cuda" or text_embeddings.device != image_embeddings.device:
+        raise RuntimeError("distributed_sigmoid_loss_b200 runs on CUDA (sm_100a) tensors only; there is no CPU path")
+    if image_embeddings.shape[1] % 8 != 0:
+        raise RuntimeError("emb_dim must be a multiple of 8 (16-byte rows for TMA)")
+
+
+class DDPSigmoidLoss(nn.Module):
+    """Drop-in for the reference ``DDPSigmoidLoss`` (distributed_sigmoid_loss.py:8-48).
+
+    ``t_prime`` (0-dim, float64 like ``torch.tensor(np.log(10))``) and ``bias`` (0-dim fp32, -10) are
+    ``nn.Parameter``s with the reference's state_dict keys; hand them to the optimizer (README.md:20).
+    Embeddings are expected L2-normalised by the caller (distributed_sigmoid_loss.py:20).
+    Every rank of ``group`` must call ``forward`` the same number of times (collective, like all_gather).
+    """
+
+    def __init__(self, gpu_batch_size: int, group=None, cta_group: int = 2, overlap_pull: bool = True) -> None:
+        super().__init__()
+        self.t_prime = nn.Parameter(torch.tensor(math.log(10), dtype=torch.float64))
+        self.bias = nn.Parameter(torch.tensor(-10.0))
+        self.gpu_batch_size = gpu_batch_size
+        self._cache = _EngineCache(group, cta_group, overlap_pull)
+
+    def engine_for(self, batch: int, dim: int, device: torch.device) -> SigmoidLossEngine:
+        return self._cache.get(batch, dim, device)
+
+    def forward(self, image_embeddings: torch.Tensor, text_embeddings: torch.Tensor) -> torch.Tensor:
+        _validate(image_embeddings, text_embeddings, self.gpu_batch_size)
+        eng = self._cache.get(image_embeddings.shape[0], image_embeddings.shape[1], image_embeddings.device)
+        return _SigmoidLossFn.apply(image_embeddings, text_embeddings, self.t_prime, self.bias, eng)
+
+
+SigmoidLoss = DDPSigmoidLoss
+
+
+class SigLipLoss(nn.Module):
+    """open_clip-signature adapter (rwightman_sigmoid_loss.py:12-124): scale and bias are passed in, the ring
+    exchange of the original is replaced by the direct NVSwitch pulls of the fused path. ``bidir`` is accepted
+    for signature parity; the visiting order of chunks does not change the result."""
+
+    def __init__(self, cache_labels: bool = False, rank: int = 0, world_size: int = 1, bidir: bool = True,
+                 use_horovod: bool = False, group=None, cta_group: int = 2):
+        super().__init__()
+        assert not use_horovod  # same restriction as the reference (rwightman_sigmoid_loss.py:35)
+        self.cache_labels, self.rank, self.world_size, self.bidir = cache_labels, rank, world_size, bidir
+        self.use_horovod = use_horovod
+        self._cache = _EngineCache(group, cta_group)
+
+    def forward(self, image_features, text_features, logit_scale, logit_bias, output_dict: bool = False):
+        _validate(image_features, text_features, None)
+        eng = self._cache.get(image_features.shape[0], image_features.shape[1], image_features.device)
+        if (eng.rank, eng.world) != (self.rank, self.world_size):
+            raise RuntimeError(
+                f"SigLipLoss(rank={self.rank}, world_size={self.world_size}) does not match the process group "
+                f"(rank={eng.rank}, world_size={eng.world})")
+        if logit_bias is None:
+            logit_bias = torch.zeros((), device=image_features.device)
+        loss = _SigmoidLossFn.apply(image_features, text_features, logit_scale, logit_bias, eng)
+        return {"contrastive_loss": loss} if output_dict else loss

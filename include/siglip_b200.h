@@ -1,0 +1,115 @@
+/*
+ * siglip_b200.h — C ABI of the B200-native distributed sigmoid (SigLIP) loss hot path.
+ *
+ * The reference (ahmdtaha/distributed_sigmoid_loss) has no FFI layer: its boundary is the Python
+ * nn.Module `DDPSigmoidLoss.forward(image_embeddings, text_embeddings)` (distributed_sigmoid_loss.py:8-48)
+ * plus torch.distributed collectives. Each entry point below names the reference code it replaces.
+ * The library never allocates or frees caller memory, never throws; every call returns 0 on success or a
+ * non-zero status whose text is available from siglip_last_error(). All device work is enqueued on the
+ * caller's stream (pass torch.cuda.current_stream().cuda_stream); nothing here synchronises the host
+ * except ctx create/destroy and handle import.
+ *
+ * Data layout: `img`, `txt` are row-major [B, D] bf16 device buffers, 16-byte aligned, D % 8 == 0.
+ * `dimg`, `dtxt` are row-major [B, D] fp32. Scalars are fp32 device scalars.
+ */
+#ifndef SIGLIP_B200_H_
+#define SIGLIP_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct siglip_ctx siglip_ctx;
+
+enum {
+  SIGLIP_OK = 0,
+  SIGLIP_ERR_INVALID = 1,   /* bad argument / shape (reference: broadcast RuntimeError when B != gpu_batch_size) */
+  SIGLIP_ERR_CUDA = 2,      /* a CUDA runtime / driver call failed */
+  SIGLIP_ERR_NO_DEVICE = 3, /* no sm_100 device: there is NO CPU fallback */
+  SIGLIP_ERR_STATE = 4      /* call sequence error (e.g. world > 1 without imported peer handles) */
+};
+
+/* tuning knobs (siglip_ctx_set_option) */
+enum {
+  SIGLIP_OPT_CTA_GROUP = 1, /* 1: cta_group::1 128x256 tiles; 2: cta_group::2 256x256 tiles per SM pair (default) */
+  SIGLIP_OPT_OVERLAP_PULL = 2 /* 1 (default): pull the next text chunk inside the loss kernel; 0: separate copy kernel */
+};
+
+/* Library / build identification: "siglip_b200 <version> sm_100a". */
+const char* siglip_version(void);
+
+/* Text of the last error on the calling thread ("" if none). */
+const char* siglip_last_error(void);
+
+/* Number of CUDA devices with compute capability 10.x visible to the process (0 on a CPU-only box). */
+int siglip_device_count(void);
+
+/*
+ * Create the per-process context: replaces DDPSigmoidLoss.__init__ (distributed_sigmoid_loss.py:9-15) —
+ * `B` is its gpu_batch_size, `rank`/`world` what dist.get_rank()/get_world_size() return at :37-38.
+ * Allocates the workspaces (gathered text [world*B, D] bf16, sigma operand [Bp, Bp] bf16, per-owner dtxt
+ * slots [world][B, D] fp32, reduction partials, flags). `device` is the CUDA device ordinal.
+ */
+int siglip_ctx_create(siglip_ctx** out, int device, int rank, int world, int B, int D);
+
+int siglip_ctx_set_option(siglip_ctx* ctx, int option, int value);
+
+/* Bytes of workspace the context holds on the device. */
+size_t siglip_ctx_workspace_bytes(const siglip_ctx* ctx);
+
+/*
+ * Peer-memory bootstrap (replaces the process-group plumbing the reference gets from
+ * dist_nn.all_gather, distributed_sigmoid_loss.py:35, and batch_isend_irecv, distributed_utils.py:24,57):
+ * each rank exports CUDA-IPC handles of its text / dtxt-slot / flag buffers; the caller all-gathers the
+ * byte strings over any transport (torch.distributed.all_gather_object) and hands the concatenation back.
+ * Not needed when world == 1.
+ */
+size_t siglip_ctx_handle_bytes(void);
+int siglip_ctx_export_handles(siglip_ctx* ctx, void* out_bytes, size_t capacity);
+int siglip_ctx_import_handles(siglip_ctx* ctx, const void* all_ranks_bytes, size_t bytes_per_rank);
+
+/*
+ * One training step of the loss: replaces DDPSigmoidLoss.forward (distributed_sigmoid_loss.py:17-48) AND
+ * the autograd backward of it, i.e. loss plus the four gradients for upstream grad 1:
+ *   loss      [1]    = (1/B) sum_ij softplus(-y_ij z_ij)
+ *   dimg      [B,D]  = dloss/dimg           (this rank's loss only)
+ *   dtxt      [B,D]  = d(sum over ranks of their losses)/dtxt   (what all_gather's backward delivers)
+ *   dt_prime  [1], dbias [1]                (this rank's loss only; DDP averages them later)
+ * Collective: every rank of the context's world must call it the same number of times.
+ */
+int siglip_fwd_bwd(siglip_ctx* ctx, const void* img, const void* txt, const float* t_prime, const float* bias,
+                   float* loss, float* dimg, float* dtxt, float* dt_prime, float* dbias, void* cuda_stream);
+
+/* Forward only (torch.no_grad / evaluation): same collective contract, no gradient work. */
+int siglip_fwd(siglip_ctx* ctx, const void* img, const void* txt, const float* t_prime, const float* bias,
+               float* loss, void* cuda_stream);
+
+/*
+ * Same step with HOST buffers (pinned or pageable): host->device copies of img/txt, the step, and
+ * device->host copies of loss (+ gradients when the pointers are non-null) all inside the call, which returns
+ * after the stream has drained. This is the end-to-end entry the benchmark times.
+ */
+int siglip_fwd_bwd_host(siglip_ctx* ctx, const void* img_host, const void* txt_host, float t_prime, float bias,
+                        float* loss_host, float* dimg_host, float* dtxt_host, float* dt_prime_host,
+                        float* dbias_host, void* cuda_stream);
+
+/* Kernels launched by the context since creation (for the benchmark's gpu_launches field). */
+unsigned long long siglip_ctx_launch_count(const siglip_ctx* ctx);
+
+/*
+ * Test hook: plain contraction C[M,N] (fp32) = A * B^T on the same tcgen05 mainloop, to pin the operand
+ * layouts independently of the loss epilogue. a_mn / b_mn: 0 = operand stored [rows][K] (K contiguous),
+ * 1 = stored [K][rows] (rows contiguous). lda/ldb/ldc in elements. cta_group 1 or 2.
+ */
+int siglip_debug_gemm(int device, int cta_group, int M, int N, int K, const void* A, long long lda, int a_mn,
+                      const void* Bm, long long ldb, int b_mn, float* C, long long ldc, void* cuda_stream);
+
+void siglip_ctx_destroy(siglip_ctx* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SIGLIP_B200_H_ */
