@@ -1,0 +1,345 @@
+#!/usr/bin/env python
+"""Benchmark of the distributed sigmoid (SigLIP) loss hot path (BASELINE.json metric).
+
+    python bench.py --gpus 1 --steps 20 --warmup 5                 # this repo's sm_100a path
+    torchrun --nproc-per-node N ... bench.py --gpus N ...          # one rank per GPU (driver launches this)
+    python bench.py --impl reference --gpus 1 --steps 5 --warmup 1 # the reference's CPU op sequence (oracle port)
+
+Workload (BASELINE.json `metric`): per-rank batch B=16384, D=1024, bf16, W = --gpus text chunks per rank,
+synthetic L2-normalised features (seed 1234 + rank), t' = log 10, b = -10. One "step" = one fused
+forward+backward of the loss module (loss + dimg + dtxt + dt' + dbias). Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "image-text pairs/sec"
+UNIT = "pairs/s"
+
+
+def _peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(path) as f:
+            p = json.load(f)
+        return float(p["bf16_tflops_sustained"]), "MEASURED_PEAKS.json bf16_tflops_sustained (of measured)"
+    except Exception:
+        return 1400.0, "B200_PROFILING.md fallback, sustained ~1.4 PFLOP/s (of fallback)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu_index = gpu_index
+        self.proc = None
+        self.lines = []
+        self.thread = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.gpu_index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+            return
+        self.thread = threading.Thread(target=self._pump, daemon=True)
+        self.thread.start()
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        clocks, maxes, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                clocks.append(float(f[1]))
+                maxes.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(names, f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        clocks.sort()
+        med = clocks[len(clocks) // 2] if clocks else None
+        return {"sm_mhz": med, "sm_max_mhz": max(maxes) if maxes else None, "reasons": sorted(reasons),
+                "samples": len(clocks)}
+
+
+def synth(rank: int, B: int, D: int):
+    import torch
+
+    g = torch.Generator().manual_seed(1234 + rank)
+    img = torch.nn.functional.normalize(torch.randn(B, D, generator=g))
+    txt = torch.nn.functional.normalize(torch.randn(B, D, generator=g))
+    return img.to(torch.bfloat16), txt.to(torch.bfloat16)
+
+
+# ------------------------------------------------------------------------------------------------------
+# CPU baseline: the reference's op sequence (oracle.port_step), bounded row sample of the same workload
+# ------------------------------------------------------------------------------------------------------
+def cpu_reference_rate(B: int, D: int, world: int, sample_rows: int, steps: int, warmup: int):
+    """Times oracle.port_step (distributed_sigmoid_loss.py:17-48 op for op, fp32 on bf16-rounded inputs, all host
+    threads) on the first `sample_rows` image rows of rank 0 against all `world` text chunks of B rows. Work is
+    linear in image rows, so pair-scores/s measured on the sample is the rate of the full step.
+    Returns (pairs_per_s for the WHOLE job on this one host, seconds per sampled step, threads)."""
+    import torch
+
+    from oracle.siglip_oracle import port_step
+
+    threads = torch.get_num_threads()
+    img, _ = synth(0, B, D)
+    img = img[:sample_rows].float()
+    chunks = [synth(c, B, D)[1].float() for c in range(world)]
+    times = []
+    for it in range(warmup + steps):
+        a = img.clone().requires_grad_(True)
+        cs = [c.clone().requires_grad_(True) for c in chunks]
+        tp = torch.tensor(math.log(10.0), dtype=torch.float64, requires_grad=True)
+        bb = torch.tensor(-10.0, requires_grad=True)
+        t0 = time.perf_counter()
+        _port_step_rect(a, cs, tp, bb)
+        dt = time.perf_counter() - t0
+        if it >= warmup:
+            times.append(dt)
+    sec = sum(times) / len(times)
+    scores_per_s = sample_rows * world * B / sec          # pair scores (logits) per second on this host
+    # whole job = world ranks x (B x world*B) scores per step, all on this host's cores
+    job_step_s = world * B * world * B / scores_per_s
+    return world * B / job_step_s, sec, threads
+
+
+def _port_step_rect(img, txt_chunks, t_prime, bias):
+    """port_step on a row sample: identical ops, labels for the sampled rows (rows 0..n-1 of rank 0's batch)."""
+    import torch
+
+    n, bsz = img.shape[0], txt_chunks[0].shape[0]
+    logsig = torch.nn.LogSigmoid()
+    total = 0
+    for c, txt in enumerate(txt_chunks):
+        t = t_prime.exp()
+        logits = img @ txt.T * t + bias
+        if c == 0:
+            labels = 2 * torch.eye(n, bsz) - torch.ones(n, bsz)
+        else:
+            labels = -1 * torch.ones(bsz)
+        total = total + (-logsig(labels * logits)).sum()
+    total = total / bsz
+    total.backward()
+    return total
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    import torch
+
+    B, D, W = args.batch, args.dim, args.gpus
+    rows = args.cpu_sample_rows
+    value, sec, threads = cpu_reference_rate(B, D, W, rows, max(1, args.steps), max(0, args.warmup))
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3 * (B / rows) * W,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"SigLIP loss fwd+bwd, B={B}/rank D={D} W={W} chunks, reference op sequence on CPU",
+                   "global_batch": B * W, "batch_per_rank": B, "dim": D, "world": W},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
+                         "sample": f"{rows} of {B} image rows of rank 0 x {W} text chunk(s) of {B} rows per step; "
+                                   f"{sec:.3f} s per sampled step; whole-job rate = sampled pair-score rate / (W*B); "
+                                   "oracle.port_step (the reference is pure Python/torch: it cannot travel to the GPU box, "
+                                   "the port executes the same torch ops, checked against it in tests/test_oracle.py)"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+# ------------------------------------------------------------------------------------------------------
+# this repo's path
+# ------------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    from distributed_sigmoid_loss_b200 import DDPSigmoidLoss, _capi
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("--gpus N > 1 must be launched with torch.distributed.run (one rank per GPU)")
+        args.gpus = world
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a B200: the product path has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    B, D, W = args.batch, args.dim, world
+    img_h, txt_h = synth(rank, B, D)
+    img = img_h.to(dev).requires_grad_(True)
+    txt = txt_h.to(dev).requires_grad_(True)
+    mod = DDPSigmoidLoss(B, cta_group=args.cta_group).to(dev)
+    eng = mod.engine_for(B, D, dev)
+
+    def step():
+        img.grad = None
+        txt.grad = None
+        mod.t_prime.grad = None
+        mod.bias.grad = None
+        loss = mod(img, txt)
+        loss.backward()
+        return loss
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+    eng.set_option(_capi.SIGLIP_OPT_KERNEL_TIMING, 1)
+    launches0 = eng.launch_count
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        loss = step()
+    e1.record()
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    ms_total = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms_total], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total = float(t)
+    ms_step = ms_total / args.steps
+    launches = eng.launch_count - launches0
+    loss_ms, loss_n, grad_ms, grad_n = eng.kernel_times()
+    eng.set_option(_capi.SIGLIP_OPT_KERNEL_TIMING, 0)
+    value = W * B / (ms_step * 1e-3)
+
+    # ---- end to end: host buffers in, loss out, through the C-ABI host entry --------------------------
+    img_p, txt_p = img_h.pin_memory(), txt_h.pin_memory()
+    for _ in range(2):
+        eng.fwd_bwd_host(img_p, txt_p, math.log(10.0), -10.0)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        eng.fwd_bwd_host(img_p, txt_p, math.log(10.0), -10.0)
+    barrier()
+    e2e_s = (time.perf_counter() - t0) / args.steps
+    if world > 1:
+        t = torch.tensor([e2e_s], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t)
+    e2e_value = W * B / e2e_s
+
+    if rank == 0:
+        peak, peak_src = _peaks()
+        # dominant kernel: the gradient kernel (two of the three contractions): 4*B*B*D flops per launch
+        flops_grad = 4.0 * B * B * D
+        flops_loss = 2.0 * B * B * D
+        grad_avg_ms = grad_ms / max(grad_n, 1)
+        loss_avg_ms = loss_ms / max(loss_n, 1)
+        achieved = flops_grad / (grad_avg_ms * 1e-3) / 1e12 if grad_n else None
+        traffic = None
+        prof = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+        if os.path.exists(prof):
+            try:
+                with open(prof) as f:
+                    traffic = json.load(f).get("grad_kernel_dram_bytes_per_launch")
+            except Exception:
+                traffic = None
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": W, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": f"SigLIP loss fused fwd+bwd, B={B}/rank D={D} bf16, W={W} text chunk(s)/rank "
+                                   "(BASELINE.json headline shape; at N=1 the single-chunk case)",
+                       "global_batch": B * W, "batch_per_rank": B, "dim": D, "world": W,
+                       "parallelism": f"dp{W}", "cta_group": args.cta_group,
+                       "l2": "no explicit flush: each step streams >1 GiB (bf16 sigma operand) through the 126 MB L2",
+                       "api": "DDPSigmoidLoss.forward + loss.backward() (torch autograd over the C ABI)"},
+            "loss": float(loss),
+            "flops_per_step_per_rank": 6.0 * B * (W * B) * D,
+            "tflops_per_gpu": 6.0 * B * (W * B) * D / (ms_step * 1e-3) / 1e12,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 2 * B * D * 2, "d2h_bytes_per_step": 12,
+                    "ms_per_step": e2e_s * 1e3,
+                    "api": "siglip_fwd_bwd_host (pinned host bf16 in, loss/dt'/dbias out, grads stay on device)"},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "roofline": {"bound": "tensor", "kernel": "siglip_gemm_kernel<cg,1> (dimg + dtxt contractions)",
+                         "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+                         "frac": (achieved / peak) if achieved else None, "peak_source": peak_src,
+                         "avg_launch_ms": grad_avg_ms, "launches_timed": grad_n, "traffic": traffic,
+                         "loss_kernel": {"achieved": flops_loss / (loss_avg_ms * 1e-3) / 1e12 if loss_n else None,
+                                         "avg_launch_ms": loss_avg_ms, "launches_timed": loss_n}},
+        }
+        if W == 1 and not args.no_cpu_baseline:
+            v, sec, threads = cpu_reference_rate(B, D, 1, args.cpu_sample_rows, 3, 1)
+            line["cpu_baseline"] = {
+                "value": v, "unit": UNIT, "cores": threads, "kind": "port",
+                "sample": f"{args.cpu_sample_rows} of {B} image rows x 1 text chunk of {B} rows, 1 warm-up + 3 timed, "
+                          f"{sec:.3f} s per sampled step; oracle.port_step = the reference's torch op sequence in fp32"}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=16384)
+    ap.add_argument("--dim", type=int, default=1024)
+    ap.add_argument("--cta-group", type=int, default=int(os.environ.get("SIGLIP_CTA_GROUP", "2")))
+    ap.add_argument("--cpu-sample-rows", type=int, default=2048)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_ours(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

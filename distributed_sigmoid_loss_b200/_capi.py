@@ -29,8 +29,13 @@ EXPORTED_SYMBOLS = (
     "siglip_fwd_bwd",
     "siglip_fwd",
     "siglip_fwd_bwd_host",
+    "siglip_ctx_kernel_times",
     "siglip_ctx_launch_count",
     "siglip_debug_gemm",
+    "siglip_debug_gemm_timed",
+    "siglip_debug_loopback",
+    "siglip_debug_set_text_chunk",
+    "siglip_debug_get_slot",
     "siglip_ctx_destroy",
 )
 
@@ -42,6 +47,10 @@ SIGLIP_ERR_STATE = 4
 
 SIGLIP_OPT_CTA_GROUP = 1
 SIGLIP_OPT_OVERLAP_PULL = 2
+SIGLIP_OPT_KERNEL_TIMING = 3
+SIGLIP_OPT_STAGES_LOSS = 4
+SIGLIP_OPT_STAGES_GRAD = 5
+SIGLIP_OPT_MCAST = 6
 
 _lib: Optional[ctypes.CDLL] = None
 
@@ -96,11 +105,23 @@ def lib() -> ctypes.CDLL:
     L.siglip_fwd.restype = ci
     L.siglip_fwd_bwd_host.argtypes = [vp, vp, vp, ctypes.c_float, ctypes.c_float, vp, vp, vp, vp, vp, vp]
     L.siglip_fwd_bwd_host.restype = ci
+    L.siglip_ctx_kernel_times.argtypes = [vp, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ci),
+                                          ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ci)]
+    L.siglip_ctx_kernel_times.restype = ci
+    L.siglip_debug_loopback.argtypes = [vp]
+    L.siglip_debug_loopback.restype = ci
+    L.siglip_debug_set_text_chunk.argtypes = [vp, ci, vp, vp]
+    L.siglip_debug_set_text_chunk.restype = ci
+    L.siglip_debug_get_slot.argtypes = [vp, ci, vp, vp]
+    L.siglip_debug_get_slot.restype = ci
     L.siglip_ctx_launch_count.argtypes = [vp]
     L.siglip_ctx_launch_count.restype = ctypes.c_ulonglong
     L.siglip_debug_gemm.argtypes = [ci, ci, ci, ci, ci, vp, ctypes.c_longlong, ci, vp, ctypes.c_longlong, ci, vp,
                                     ctypes.c_longlong, vp]
     L.siglip_debug_gemm.restype = ci
+    L.siglip_debug_gemm_timed.argtypes = [ci, ci, ci, ci, ci, vp, ctypes.c_longlong, ci, vp, ctypes.c_longlong, ci, vp,
+                                          ctypes.c_longlong, ci, ctypes.POINTER(ctypes.c_float), vp]
+    L.siglip_debug_gemm_timed.restype = ci
     L.siglip_ctx_destroy.argtypes = [vp]
     L.siglip_ctx_destroy.restype = None
     _lib = L

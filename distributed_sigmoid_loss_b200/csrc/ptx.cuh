@@ -93,14 +93,23 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
 #define SIGLIP_WAIT_TIMEOUT_NS 4000000000ull  // 4 s: any legitimate in-kernel wait is < 100 ms
 #endif
 
+__device__ __forceinline__ long long clock_cycles() {
+  long long c;
+  asm volatile("mov.u64 %0, %%clock64;" : "=l"(c));
+  return c;
+}
+
 // Bounded wait: a protocol bug must not hang the GPU. On timeout the site id is published to the
 // host-mapped debug record and the kernel traps (the launch then fails loudly on the host).
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, DebugRecord* dbg, uint32_t site,
-                                          uint32_t aux0 = 0, uint32_t aux1 = 0) {
+                                          uint32_t aux0 = 0, uint32_t aux1 = 0, uint32_t sleep_ns = 0,
+                                          long long* waited = nullptr) {
   if (mbar_try_wait(bar, parity)) return;
+  const long long c0 = waited ? clock_cycles() : 0;
   uint64_t t0 = 0;
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
+    if (sleep_ns) __nanosleep(sleep_ns);  // long waits (epilogue warps during a K loop): do not burn issue slots
     if ((++spins & 0x3ffu) == 0) {
       uint64_t now = globaltimer_ns();
       if (t0 == 0) t0 = now;
@@ -118,6 +127,7 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, DebugRe
       }
     }
   }
+  if (waited) *waited += clock_cycles() - c0;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -144,6 +154,17 @@ __device__ __forceinline__ void tma_load_2d(const CUtensorMap* m, uint32_t bar, 
         "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1)
         : "memory");
   }
+}
+
+// Same load, delivered to the same shared-memory offset of every CTA in `cta_mask` of the cluster; each
+// destination CTA's barrier at offset `bar` receives the complete_tx. One L2 read feeds all destinations.
+__device__ __forceinline__ void tma_load_2d_mcast(const CUtensorMap* m, uint32_t bar, uint32_t dst, int c0, int c1,
+                                                  uint16_t cta_mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster"
+      " [%0], [%1, {%4, %5}], [%2], %3;" ::"r"(dst),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "h"(cta_mask), "r"(c0), "r"(c1)
+      : "memory");
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -208,6 +229,15 @@ __device__ __forceinline__ void umma_commit(uint32_t bar) {
         "h"(mask)
         : "memory");
   }
+}
+
+// cta_group::1 commit whose arrive is delivered to the same barrier offset in every CTA of `cta_mask`
+// (frees a multicast-fed smem stage in all CTAs that write into it).
+__device__ __forceinline__ void umma_commit_mcast(uint32_t bar, uint16_t cta_mask) {
+  asm volatile(
+      "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+      "h"(cta_mask)
+      : "memory");
 }
 
 // TMEM -> registers: this warp's 32 lanes x 32 consecutive fp32 columns (one row per thread).

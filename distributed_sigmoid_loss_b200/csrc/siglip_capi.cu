@@ -4,6 +4,7 @@
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <string>
@@ -66,7 +67,7 @@ EncodeTiledFn get_encode_fn() {
 
 // bf16 2-D tensor, `inner` contiguous elements per row, rows `row_stride_elems` apart; 128B-swizzled boxes.
 int encode_bf16_2d(CUtensorMap* m, const void* base, uint64_t inner, uint64_t outer, uint64_t row_stride_elems,
-                   uint32_t box_inner, uint32_t box_outer) {
+                   uint32_t box_inner, uint32_t box_outer, CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B) {
   EncodeTiledFn fn = get_encode_fn();
   if (fn == nullptr) return fail(SIGLIP_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
   if ((reinterpret_cast<uintptr_t>(base) & 15u) != 0) return fail(SIGLIP_ERR_INVALID, "operand not 16-byte aligned");
@@ -76,7 +77,7 @@ int encode_bf16_2d(CUtensorMap* m, const void* base, uint64_t inner, uint64_t ou
   cuuint32_t box[2] = {box_inner, box_outer};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     char buf[256];
@@ -136,6 +137,13 @@ struct siglip_ctx {
   DebugRecord* dbg_dev = nullptr;
   unsigned long long launches = 0;
   size_t workspace_bytes = 0;
+  // optional per-kernel CUDA-event timing (SIGLIP_OPT_KERNEL_TIMING): pairs recorded on the caller's stream
+  int kernel_timing = 0;
+  int stages_loss = 0, stages_grad = 0;  // 0 = kernel default
+  int mcast = 2;                         // B-tile multicast cluster size for cta_group 1 (1 = off)
+  std::vector<cudaEvent_t> ev_loss, ev_grad;  // start, stop, start, stop, ...
+  size_t ev_loss_used = 0, ev_grad_used = 0;
+  bool loopback = false;
   // host-API staging
   __nv_bfloat16* h_img = nullptr;
   __nv_bfloat16* h_txt = nullptr;
@@ -156,6 +164,17 @@ int check_dbg(siglip_ctx* c, const char* where) {
   return 0;
 }
 
+int timing_mark(siglip_ctx* c, std::vector<cudaEvent_t>& evs, size_t& used, cudaStream_t st) {
+  if (!c->kernel_timing) return 0;
+  if (used == evs.size()) {
+    cudaEvent_t e;
+    CK(cudaEventCreate(&e));
+    evs.push_back(e);
+  }
+  CK(cudaEventRecord(evs[used++], st));
+  return 0;
+}
+
 // The loss kernel over one text chunk: S = img @ txt_c^T on tcgen05, fused scale/bias/log-sigmoid/reduce.
 int run_loss_chunk(siglip_ctx* c, const void* img, const __nv_bfloat16* txt_c, const float* t_prime,
                    const float* bias, bool own, bool store_g, bool accumulate, const void* pull_src, void* pull_dst,
@@ -165,7 +184,8 @@ int run_loss_chunk(siglip_ctx* c, const void* img, const __nv_bfloat16* txt_c, c
   CUtensorMap tmA, tmB;
   int rc;
   if ((rc = encode_operand(&tmA, img, c->B, c->D, c->D, 0, 128))) return rc;
-  if ((rc = encode_operand(&tmB, txt_c, c->B, c->D, c->D, 0, 256 / cg))) return rc;
+  const int mc = (cg == 1) ? c->mcast : 1;
+  if ((rc = encode_operand(&tmB, txt_c, c->B, c->D, c->D, 0, 256 / (cg * mc)))) return rc;
   KernelParams p;
   memset(&p, 0, sizeof(p));
   p.nprob = 1;
@@ -190,7 +210,15 @@ int run_loss_chunk(siglip_ctx* c, const void* img, const __nv_bfloat16* txt_c, c
   p.pull_bytes = pull_bytes;
   p.pull_wait_flag = pull_flag;
   p.pull_wait_value = pull_value;
-  CKI(siglip::launch_gemm(cg, siglip::kModeLoss, &tmA, &tmB, &tmA, &tmB, p, c->num_sms, st));
+  // store map of the sigma operand: [B, B] bf16 inside the padded [Bp, Bp] buffer, one 32x32 slab per TMA store
+  CUtensorMap tmG;
+  if ((rc = encode_bf16_2d(&tmG, c->G, (uint64_t)c->B, (uint64_t)c->B, (uint64_t)c->Bp, 32, 32,
+                           CU_TENSOR_MAP_SWIZZLE_64B)))
+    return rc;
+  if ((rc = timing_mark(c, c->ev_loss, c->ev_loss_used, st))) return rc;
+  CKI(siglip::launch_gemm(cg, siglip::kModeLoss, c->stages_loss, mc, &tmA, &tmB, &tmA, &tmB, &tmG, p, c->num_sms,
+                          st));
+  if ((rc = timing_mark(c, c->ev_loss, c->ev_loss_used, st))) return rc;
   c->launches++;
   return 0;
 }
@@ -234,7 +262,10 @@ int run_grad_chunk(siglip_ctx* c, const void* img, const __nv_bfloat16* txt_c, c
   p.t_prime = t_prime;
   p.inv_b = 1.0f / static_cast<float>(c->B);
   p.dbg = c->dbg_dev;
-  CKI(siglip::launch_gemm(cg, siglip::kModeOut, &tmA0, &tmB0, &tmA1, &tmB1, p, c->num_sms, st));
+  if ((rc = timing_mark(c, c->ev_grad, c->ev_grad_used, st))) return rc;
+  CKI(siglip::launch_gemm(cg, siglip::kModeOut, c->stages_grad, (cg == 1) ? c->mcast : 1, &tmA0, &tmB0, &tmA1, &tmB1,
+                          &tmA0, p, c->num_sms, st));
+  if ((rc = timing_mark(c, c->ev_grad, c->ev_grad_used, st))) return rc;
   c->launches++;
   return 0;
 }
@@ -273,7 +304,6 @@ int step_impl(siglip_ctx* c, const void* img, const void* txt, const float* t_pr
     // peers must have finished reading my text slot / dtxt slots of the previous step before I overwrite them
     if ((rc = wait_peers(c, 2, s - 1, st))) return rc;
     CK(cudaMemcpyAsync(c->txt_all + r * chunk_elems, txt, chunk_bytes, cudaMemcpyDeviceToDevice, st));
-    c->launches++;
     if ((rc = signal_peers(c, 0, s, st))) return rc;
     own_txt = c->txt_all + r * chunk_elems;
   }
@@ -302,7 +332,6 @@ int step_impl(siglip_ctx* c, const void* img, const void* txt, const float* t_pr
       // un-overlapped variant (for A/B measurements): wait + copy as separate stream operations
       if ((rc = wait_peers(c, 0, s, st))) return rc;
       CK(cudaMemcpyAsync(pull_dst, pull_src, pull_bytes, cudaMemcpyDefault, st));
-      c->launches++;
       pull_bytes = 0;
       pull_src = pull_dst = nullptr;
       pull_flag = nullptr;
@@ -423,6 +452,20 @@ int siglip_ctx_set_option(siglip_ctx* c, int option, int value) {
     case SIGLIP_OPT_OVERLAP_PULL:
       c->overlap_pull = value ? 1 : 0;
       return 0;
+    case SIGLIP_OPT_MCAST:
+      if (value != 1 && value != 2) return fail(SIGLIP_ERR_INVALID, "mcast must be 1 or 2");
+      c->mcast = value;
+      return 0;
+    case SIGLIP_OPT_STAGES_LOSS:
+      c->stages_loss = value;
+      return 0;
+    case SIGLIP_OPT_STAGES_GRAD:
+      c->stages_grad = value;
+      return 0;
+    case SIGLIP_OPT_KERNEL_TIMING:
+      c->kernel_timing = value ? 1 : 0;
+      c->ev_loss_used = c->ev_grad_used = 0;
+      return 0;
     default:
       return fail(SIGLIP_ERR_INVALID, "unknown option");
   }
@@ -529,10 +572,80 @@ int siglip_fwd_bwd_host(siglip_ctx* c, const void* img_host, const void* txt_hos
   return 0;
 }
 
+int siglip_ctx_kernel_times(siglip_ctx* c, double* loss_ms, int* loss_launches, double* grad_ms, int* grad_launches) {
+  if (c == nullptr) return fail(SIGLIP_ERR_INVALID, "ctx is null");
+  CK(cudaSetDevice(c->device));
+  CK(cudaDeviceSynchronize());
+  double tl = 0.0, tg = 0.0;
+  for (size_t i = 0; i + 1 < c->ev_loss_used; i += 2) {
+    float ms = 0.f;
+    CK(cudaEventElapsedTime(&ms, c->ev_loss[i], c->ev_loss[i + 1]));
+    tl += ms;
+  }
+  for (size_t i = 0; i + 1 < c->ev_grad_used; i += 2) {
+    float ms = 0.f;
+    CK(cudaEventElapsedTime(&ms, c->ev_grad[i], c->ev_grad[i + 1]));
+    tg += ms;
+  }
+  if (loss_ms) *loss_ms = tl;
+  if (grad_ms) *grad_ms = tg;
+  if (loss_launches) *loss_launches = static_cast<int>(c->ev_loss_used / 2);
+  if (grad_launches) *grad_launches = static_cast<int>(c->ev_grad_used / 2);
+  c->ev_loss_used = c->ev_grad_used = 0;
+  return 0;
+}
+
+int siglip_debug_loopback(siglip_ctx* c) {
+  if (c == nullptr) return fail(SIGLIP_ERR_INVALID, "ctx is null");
+  if (c->world == 1) return fail(SIGLIP_ERR_STATE, "loopback needs world > 1");
+  CK(cudaSetDevice(c->device));
+  const size_t chunk_elems = static_cast<size_t>(c->B) * c->D;
+  for (int p = 0; p < c->world; ++p) {
+    c->peer_txt[p] = c->txt_all;
+    c->peer_slots[p] = c->slots;
+    c->peer_flags[p] = c->flags;
+  }
+  std::vector<const float*> red(c->world);
+  for (int p = 0; p < c->world; ++p) red[p] = c->slots + c->rank * chunk_elems;
+  CK(cudaMemcpy(c->reduce_ptrs_dev, red.data(), c->world * sizeof(float*), cudaMemcpyHostToDevice));
+  std::vector<unsigned int*> sig(kFlagKinds * c->world);
+  for (int k = 0; k < kFlagKinds; ++k)
+    for (int p = 0; p < c->world; ++p) sig[k * c->world + p] = c->flags + k * kMaxWorld + p;
+  CK(cudaMemcpy(c->signal_ptrs_dev, sig.data(), sig.size() * sizeof(unsigned int*), cudaMemcpyHostToDevice));
+  c->peers_ready = true;
+  c->loopback = true;
+  return 0;
+}
+
+int siglip_debug_set_text_chunk(siglip_ctx* c, int chunk, const void* txt_dev, void* cuda_stream) {
+  if (c == nullptr || txt_dev == nullptr) return fail(SIGLIP_ERR_INVALID, "null argument");
+  if (c->world == 1 || chunk < 0 || chunk >= c->world) return fail(SIGLIP_ERR_INVALID, "chunk out of range");
+  const size_t chunk_elems = static_cast<size_t>(c->B) * c->D;
+  CK(cudaMemcpyAsync(c->txt_all + chunk * chunk_elems, txt_dev, chunk_elems * sizeof(__nv_bfloat16),
+                     cudaMemcpyDeviceToDevice, static_cast<cudaStream_t>(cuda_stream)));
+  return 0;
+}
+
+int siglip_debug_get_slot(siglip_ctx* c, int chunk, float* out_dev, void* cuda_stream) {
+  if (c == nullptr || out_dev == nullptr) return fail(SIGLIP_ERR_INVALID, "null argument");
+  if (c->world == 1 || chunk < 0 || chunk >= c->world) return fail(SIGLIP_ERR_INVALID, "chunk out of range");
+  const size_t chunk_elems = static_cast<size_t>(c->B) * c->D;
+  CK(cudaMemcpyAsync(out_dev, c->slots + chunk * chunk_elems, chunk_elems * sizeof(float), cudaMemcpyDeviceToDevice,
+                     static_cast<cudaStream_t>(cuda_stream)));
+  return 0;
+}
+
 unsigned long long siglip_ctx_launch_count(const siglip_ctx* c) { return c ? c->launches : 0ull; }
 
 int siglip_debug_gemm(int device, int cta_group, int M, int N, int K, const void* A, long long lda, int a_mn,
                       const void* Bm, long long ldb, int b_mn, float* C, long long ldc, void* cuda_stream) {
+  return siglip_debug_gemm_timed(device, cta_group, M, N, K, A, lda, a_mn, Bm, ldb, b_mn, C, ldc, 1, nullptr,
+                                 cuda_stream);
+}
+
+int siglip_debug_gemm_timed(int device, int cta_group, int M, int N, int K, const void* A, long long lda, int a_mn,
+                            const void* Bm, long long ldb, int b_mn, float* C, long long ldc, int iters,
+                            float* ms_per_iter, void* cuda_stream) {
   if (A == nullptr || Bm == nullptr || C == nullptr) return fail(SIGLIP_ERR_INVALID, "null argument");
   if (cta_group != 1 && cta_group != 2) return fail(SIGLIP_ERR_INVALID, "cta_group must be 1 or 2");
   if (M < 1 || N < 4 || K < 1 || (N % 4) != 0) return fail(SIGLIP_ERR_INVALID, "need N % 4 == 0");
@@ -544,7 +657,9 @@ int siglip_debug_gemm(int device, int cta_group, int M, int N, int K, const void
   CUtensorMap tmA, tmB;
   int rc;
   if ((rc = encode_operand(&tmA, A, M, K, lda, a_mn, 128))) return rc;
-  if ((rc = encode_operand(&tmB, Bm, N, K, ldb, b_mn, 256 / cta_group))) return rc;
+  const char* env_mc = getenv("SIGLIP_DEBUG_MCAST");
+  const int mcast = (cta_group == 1 && env_mc) ? atoi(env_mc) : 1;
+  if ((rc = encode_operand(&tmB, Bm, N, K, ldb, b_mn, 256 / (cta_group * mcast)))) return rc;
   float* zero = nullptr;  // t' = 0 -> scale exp(0) * 1 = 1
   CK(cudaMalloc(reinterpret_cast<void**>(&zero), sizeof(float)));
   CK(cudaMemsetAsync(zero, 0, sizeof(float), st));
@@ -568,8 +683,58 @@ int siglip_debug_gemm(int device, int cta_group, int M, int N, int K, const void
   p.t_prime = zero;
   p.inv_b = 1.0f;
   p.dbg = dbg_dev;
-  int lrc = siglip::launch_gemm(cta_group, siglip::kModeOut, &tmA, &tmB, &tmA, &tmB, p, num_sms, st);
+  cudaEvent_t e0, e1;
+  CK(cudaEventCreate(&e0));
+  CK(cudaEventCreate(&e1));
+  int lrc = 0;
+  unsigned long long* wstats = nullptr;
+  if (getenv("SIGLIP_DEBUG_WAITSTATS")) {
+    printf("[waitstats cg=%d] max co-resident clusters: %d (SMs %d)\n", cta_group,
+           siglip::query_max_active_clusters(cta_group), num_sms);
+    CK(cudaMalloc(reinterpret_cast<void**>(&wstats), 8 * 256 * sizeof(unsigned long long)));
+    CK(cudaMemsetAsync(wstats, 0, 8 * 256 * sizeof(unsigned long long), st));
+    p.wait_stats = wstats;
+  }
+  const char* env_sl = getenv("SIGLIP_DEBUG_EPI_SLEEP");
+  p.epi_sleep_ns = env_sl ? static_cast<unsigned int>(atoi(env_sl)) : 0u;
+  const char* env_st = getenv("SIGLIP_DEBUG_STAGES");
+  const int stages = env_st ? atoi(env_st) : 0;
+  if (iters > 1)  // warm-up
+    lrc = siglip::launch_gemm(cta_group, siglip::kModeOut, stages, mcast, &tmA, &tmB, &tmA, &tmB, &tmA, p, num_sms, st);
+  cudaEventRecord(e0, st);
+  for (int it = 0; it < iters && lrc == 0; ++it)
+    lrc = siglip::launch_gemm(cta_group, siglip::kModeOut, stages, mcast, &tmA, &tmB, &tmA, &tmB, &tmA, p, num_sms, st);
+  cudaEventRecord(e1, st);
   cudaError_t se = cudaStreamSynchronize(st);
+  if (ms_per_iter != nullptr && se == cudaSuccess && lrc == 0) {
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    *ms_per_iter = ms / static_cast<float>(iters > 0 ? iters : 1);
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  if (wstats != nullptr) {
+    std::vector<unsigned long long> h(8 * 256);
+    cudaMemcpy(h.data(), wstats, h.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
+    double s[6] = {0, 0, 0, 0, 0, 0};
+    int nlead = 0, nall = 0;
+    for (int b = 0; b < 256; ++b) {
+      if (h[8 * b + 0] || h[8 * b + 3]) nall++;
+      s[0] += static_cast<double>(h[8 * b + 0]);
+      if (h[8 * b + 3]) {
+        nlead++;
+        for (int j = 1; j < 6; ++j) s[j] += static_cast<double>(h[8 * b + j]);
+      }
+    }
+    const double tot = s[3] > 0 ? s[3] : 1;
+    printf("[waitstats cg=%d] producer empty-wait avg %.0f cyc (%d CTAs); MMA thread (%d issuers): loop %.0f cyc = "
+           "full-wait %.1f%% + tmem-wait %.1f%% + mma-issue %.1f%% + commit %.1f%% + other %.1f%%\n",
+           cta_group, s[0] / (nall ? nall : 1), nall, nlead, s[3] / (nlead ? nlead : 1), 100.0 * s[1] / tot,
+           100.0 * s[2] / tot, 100.0 * s[4] / tot, 100.0 * s[5] / tot,
+           100.0 * (s[3] - s[1] - s[2] - s[4] - s[5]) / tot);
+    fflush(stdout);
+    cudaFree(wstats);
+  }
   int result = 0;
   if (dbg_host->code != 0) {
     char buf[256];
@@ -611,6 +776,8 @@ void siglip_ctx_destroy(siglip_ctx* c) {
   cudaFree(c->h_dimg);
   cudaFree(c->h_dtxt);
   if (c->dbg_host) cudaFreeHost(c->dbg_host);
+  for (cudaEvent_t e : c->ev_loss) cudaEventDestroy(e);
+  for (cudaEvent_t e : c->ev_grad) cudaEventDestroy(e);
   cudaGetLastError();
   delete c;
 }

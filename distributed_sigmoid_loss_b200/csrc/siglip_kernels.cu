@@ -25,23 +25,31 @@ constexpr int kBlockM = 128;   // accumulator rows per CTA (= TMEM lanes)
 constexpr int kTileN = 256;    // accumulator columns per tile (= UMMA N)
 constexpr int kBlockK = 64;    // 64 bf16 = one 128-byte swizzle row
 constexpr int kUmmaK = 16;
-constexpr int kNumEpiWarps = 8;
-constexpr int kProducerWarp = 8;
-constexpr int kMmaWarp = 9;
-constexpr int kAllocWarp = 10;  // warps 10 and 11 also run the optional peer pull
-constexpr int kNumThreads = 384;
+constexpr int kNumEpiWarps = 16;                       // 4 per TMEM lane quarter -> 4 resident per SM sub-partition
+constexpr int kEpiColGroups = kNumEpiWarps / 4;        // column groups of the 256-column accumulator
+constexpr int kEpiCols = 256 / kEpiColGroups;          // columns per epilogue warp (64)
+constexpr int kSlabsPerWarp = kEpiCols / 32;           // 32-column TMEM loads per warp per tile (2)
+constexpr int kProducerWarp = kNumEpiWarps;
+constexpr int kMmaWarp = kNumEpiWarps + 1;
+constexpr int kAllocWarp = kNumEpiWarps + 2;           // this warp and the next also run the optional peer pull
+constexpr int kNumThreads = (kNumEpiWarps + 4) * 32;
 constexpr int kAccStages = 2;
 constexpr int kTmemCols = 512;
 
-template <int kCG>
+constexpr int kStagingBytesPerWarp = 2048;  // one 32x32 bf16 slab, 64-byte rows, 64B-swizzled (TMA store source)
+
+template <int kCG, int kMode, int kStagesT>
 struct Cfg {
   static constexpr int kTileM = kBlockM * kCG;
   static constexpr int kBRows = kTileN / kCG;                      // B-operand rows held by each CTA
   static constexpr int kABytes = kBlockM * kBlockK * 2;            // 16 KiB
   static constexpr int kBBytes = kBRows * kBlockK * 2;             // 32 / 16 KiB
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kStages = (kCG == 1) ? 4 : 6;
-  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*barriers*/ + 1024 /*alignment slack*/;
+  static constexpr int kStages = kStagesT;
+  static constexpr int kStagingBytes = (kMode == kModeLoss) ? kNumEpiWarps * kStagingBytesPerWarp : 0;
+  static constexpr int kSmemBytes =
+      kStages * kStageBytes + kStagingBytes + 1024 /*barriers*/ + 1024 /*alignment slack*/;
+  static_assert(kSmemBytes <= 232448, "exceeds the 227 KB of shared memory a CTA may use");
 };
 
 constexpr float kLog2e = 1.4426950408889634f;
@@ -82,23 +90,99 @@ struct TileCoord {
   int n_blk;
 };
 
-__device__ __forceinline__ TileCoord decode_tile(const KernelParams& p, int t) {
+// Work unit of a cluster: kMC vertically adjacent tiles (same n block, consecutive m blocks) — one per CTA (pair)
+// of the cluster, so that the B operand tile is common and can be TMA-multicast.
+template <int kMC>
+__device__ __forceinline__ int cluster_tiles(const Problem& pr) {
+  return ((pr.tiles_m + kMC - 1) / kMC) * pr.tiles_n;
+}
+
+template <int kMC>
+__device__ __forceinline__ TileCoord decode_tile(const KernelParams& p, int t, int mc_rank) {
   TileCoord c;
-  const int t0 = p.prob[0].tiles_m * p.prob[0].tiles_n;
+  const int t0 = cluster_tiles<kMC>(p.prob[0]);
   c.prob = (t >= t0) ? 1 : 0;
   const int tt = c.prob ? t - t0 : t;
   const int tn = p.prob[c.prob].tiles_n;
-  c.m_blk = tt / tn;
-  c.n_blk = tt - c.m_blk * tn;
+  const int mrow = tt / tn;
+  c.m_blk = mrow * kMC + mc_rank;   // may be >= tiles_m for the last row when tiles_m is odd: fully masked tile
+  c.n_blk = tt - mrow * tn;
   return c;
 }
 
 // -------------------------------------------------------------------------------------------------
 // Epilogue of the loss kernel: one 32-column slab of one accumulator row per thread.
+//
+// Per element (s = <img_i, txt_j>, z = t*s + b, reference distributed_sigmoid_loss.py:24-33):
+//   negative pair: term = softplus(z),  g = dterm/dz = sigma(z)
+//   positive pair: term = softplus(-z), g = -sigma(-z)            (own chunk diagonal only)
+// Sums kept per thread: sum term, sum g, sum g*s (-> loss, dbias, dt').
+//
+// Fast path (whole warp slab has z < kFastZ, i.e. e = exp(z) < 2^-6, which is where a SigLIP batch lives:
+// bias ~ -10): 2 MUFU (ex2, rcp) + 10 FMA-pipe ops per element, log1p by its alternating series.
+// General path: any z, exp(-|z|) + degree-7 log1p polynomial + rcp.
 // -------------------------------------------------------------------------------------------------
+constexpr float kFastZ = -4.2f;  // e < 0.015 < 2^-6: series truncation e^4/5 < 1.1e-8 relative
+
+// The sigma slab goes to HBM through shared memory + one TMA store per warp: 4 conflict-free 16-byte
+// st.shared per thread instead of 4 strided 16-byte global stores (32 cache lines per instruction).
+struct GStore {
+  const CUtensorMap* tmap;  // bf16 [B, B] tensor, box {32 cols, 32 rows}, SWIZZLE_64B
+  uint32_t stage;           // this warp's 2 KiB staging buffer (shared::cta address, 512-byte aligned)
+  int row0;                 // first row of this warp's 32-row block
+  int lane;
+};
+
+__device__ __forceinline__ void store_g_slab(const GStore& gs, int col0, const uint32_t (&packed)[16]) {
+  // the previous TMA store of this warp must have finished READING the staging buffer
+  if (gs.lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+  __syncwarp();
+  const uint32_t row_addr = gs.stage + static_cast<uint32_t>(gs.lane) * 64u;
+  const uint32_t sw = (static_cast<uint32_t>(gs.lane) >> 1) & 3u;   // 64B swizzle: 16-byte chunk ^= (row / 2) % 4
+#pragma unroll
+  for (uint32_t c = 0; c < 4; ++c) {
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(row_addr + ((c ^ sw) << 4)), "r"(packed[4 * c + 0]),
+                 "r"(packed[4 * c + 1]), "r"(packed[4 * c + 2]), "r"(packed[4 * c + 3])
+                 : "memory");
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the TMA engine
+  __syncwarp();
+  if (gs.lane == 0) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                     reinterpret_cast<uint64_t>(gs.tmap)),
+                 "r"(gs.stage), "r"(col0), "r"(gs.row0)
+                 : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+  }
+}
+
+__device__ __forceinline__ void loss_slab_fast(const uint32_t (&v)[32], float tl, float bl, int col0, bool store_g,
+                                               const GStore& gst, float& acc_sp, float& acc_g, float& acc_gs) {
+  uint32_t packed[16];
+  float g_prev = 0.f;
+#pragma unroll
+  for (int j = 0; j < 32; ++j) {
+    const float s = __uint_as_float(v[j]);
+    const float e = ex2_approx(fmaf(s, tl, bl));       // exp(z), z < 0
+    const float g = e * rcp_approx(1.0f + e);           // sigma(z)
+    float p = fmaf(e, -0.25f, 0.33333334f);             // log1p(e) = e*(1 - e*(1/2 - e*(1/3 - e/4)))
+    p = fmaf(-e, p, 0.5f);
+    p = fmaf(-e, p, 1.0f);
+    acc_sp = fmaf(e, p, acc_sp);
+    acc_g += g;
+    acc_gs = fmaf(g, s, acc_gs);
+    if (j & 1) {
+      packed[j >> 1] = pack_bf16x2(g_prev, g);
+    } else {
+      g_prev = g;
+    }
+  }
+  if (store_g) store_g_slab(gst, col0, packed);
+}
+
 template <bool kEdge, bool kDiag>
 __device__ __forceinline__ void loss_slab(const uint32_t (&v)[32], float t, float b, int row, int col0, int nrows,
-                                          int ncols, bool store_g, __nv_bfloat16* g_row, float* g_diag,
+                                          int ncols, bool store_g, const GStore& gst, float* g_diag,
                                           float& acc_sp, float& acc_g, float& acc_gs) {
   uint32_t packed[16];
   float g_prev = 0.f;
@@ -137,13 +221,7 @@ __device__ __forceinline__ void loss_slab(const uint32_t (&v)[32], float t, floa
       g_prev = g_store;
     }
   }
-  if (store_g) {
-    uint4* dst = reinterpret_cast<uint4*>(g_row + col0);
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      dst[q] = make_uint4(packed[4 * q + 0], packed[4 * q + 1], packed[4 * q + 2], packed[4 * q + 3]);
-    }
-  }
+  if (store_g) store_g_slab(gst, col0, packed);
 }
 
 // Epilogue of the out kernel: one 32-column slab.
@@ -190,16 +268,17 @@ __device__ __forceinline__ void out_slab(const uint32_t (&v)[32], float scale, i
 // -------------------------------------------------------------------------------------------------
 // The kernel
 // -------------------------------------------------------------------------------------------------
-template <int kCG, int kMode>
+template <int kCG, int kMode, int kStagesT, int kMC>
 __global__ void __launch_bounds__(kNumThreads, 1)
 siglip_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmB0,
                    const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmB1,
-                   const __grid_constant__ KernelParams p) {
-  using C = Cfg<kCG>;
+                   const __grid_constant__ CUtensorMap tmG, const __grid_constant__ KernelParams p) {
+  using C = Cfg<kCG, kMode, kStagesT>;
   extern __shared__ uint8_t smem_raw[];
   // 128B swizzle needs 1024-byte aligned stage bases
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t bar_base = smem_base + C::kStages * C::kStageBytes;
+  const uint32_t staging_base = smem_base + C::kStages * C::kStageBytes;
+  const uint32_t bar_base = staging_base + C::kStagingBytes;
   // barrier map (8 bytes each)
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (C::kStages + s); };
@@ -210,11 +289,15 @@ siglip_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_consta
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const uint32_t cta_rank = (kCG == 2) ? cluster_ctarank() : 0u;
-  const int cluster_id = blockIdx.x / kCG;
-  const int num_clusters = gridDim.x / kCG;
-  const int total_tiles = p.prob[0].tiles_m * p.prob[0].tiles_n +
-                          (p.nprob > 1 ? p.prob[1].tiles_m * p.prob[1].tiles_n : 0);
+  static_assert(kMC == 1 || kCG == 1, "operand multicast is implemented for cta_group::1 clusters");
+  constexpr int kClusterSize = kCG * kMC;
+  const uint32_t crank = (kClusterSize > 1) ? cluster_ctarank() : 0u;
+  const uint32_t cta_rank = (kCG == 2) ? crank : 0u;      // rank inside the MMA pair
+  const int mc_rank = (kMC > 1) ? static_cast<int>(crank) : 0;  // which of the cluster's tiles this CTA computes
+  constexpr uint16_t kMcMask = static_cast<uint16_t>((1u << kMC) - 1u);
+  const int cluster_id = blockIdx.x / kClusterSize;
+  const int num_clusters = gridDim.x / kClusterSize;
+  const int total_tiles = cluster_tiles<kMC>(p.prob[0]) + (p.nprob > 1 ? cluster_tiles<kMC>(p.prob[1]) : 0);
 
   if (warp == kProducerWarp && lane == 0) {
     prefetch_tmap(&tmA0);
@@ -227,7 +310,7 @@ siglip_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_consta
   if (warp == kMmaWarp && lane == 0) {
     for (int s = 0; s < C::kStages; ++s) {
       mbar_init(full_bar(s), 1);
-      mbar_init(empty_bar(s), 1);
+      mbar_init(empty_bar(s), kMC);   // every CTA that multicasts into this stage must see it released by all readers
     }
     for (int a = 0; a < kAccStages; ++a) {
       mbar_init(tmem_full_bar(a), 1);
@@ -239,7 +322,7 @@ siglip_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_consta
     tmem_alloc<kCG>(tmem_ptr_smem, kTmemCols);
   }
   tc_fence_before();
-  if constexpr (kCG == 2) {
+  if constexpr (kClusterSize > 1) {
     cluster_sync_all();
   } else {
     __syncthreads();
@@ -250,57 +333,83 @@ siglip_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_consta
 
   if (warp == kProducerWarp) {
     // ===================================== TMA producer =====================================
-    if (lane == 0) {
+    // The whole warp runs the loop (warp-uniform control flow keeps descriptors and barrier addresses in uniform
+    // registers); one elected lane issues the TMA instructions.
+    {
       int stage = 0;
       uint32_t phase = 0;
+      long long w_empty = 0;
       const uint32_t full_owner_rank = 0;  // the pair's leader CTA owns the "full" barriers
       for (int t = cluster_id; t < total_tiles; t += num_clusters) {
-        const TileCoord tc = decode_tile(p, t);
+        const TileCoord tc = decode_tile<kMC>(p, t, mc_rank);
         const Problem& pr = p.prob[tc.prob];
         const CUtensorMap* tmA = tc.prob ? &tmA1 : &tmA0;
         const CUtensorMap* tmB = tc.prob ? &tmB1 : &tmB0;
         const int m_idx = tc.m_blk * C::kTileM + static_cast<int>(cta_rank) * kBlockM;
         const int n_idx = tc.n_blk * kTileN + static_cast<int>(cta_rank) * C::kBRows;
         const int num_kb = (pr.K + kBlockK - 1) / kBlockK;
+        const int a_mn = pr.a_mn, b_mn = pr.b_mn;
         for (int kb = 0; kb < num_kb; ++kb) {
-          mbar_wait(empty_bar(stage), phase ^ 1u, p.dbg, 1, t, kb);
-          const uint32_t sA = smem_base + stage * C::kStageBytes;
-          const uint32_t sB = sA + C::kABytes;
-          uint32_t fb = full_bar(stage);
-          if (cta_rank == 0) mbar_arrive_expect_tx(fb, C::kStageBytes * kCG);
-          if constexpr (kCG == 2) fb = mapa_shared(fb, full_owner_rank);
-          const int k_idx = kb * kBlockK;
-          if (!pr.a_mn) {
-            tma_load_2d<kCG>(tmA, fb, sA, k_idx, m_idx);  // box {64 k, 128 rows}
-          } else {
+          mbar_wait(empty_bar(stage), phase ^ 1u, p.dbg, 1, t, kb, 0, p.wait_stats ? &w_empty : nullptr);
+          if (elect_one_sync()) {
+            const uint32_t sA = smem_base + stage * C::kStageBytes;
+            const uint32_t sB = sA + C::kABytes;
+            uint32_t fb = full_bar(stage);
+            if (cta_rank == 0) mbar_arrive_expect_tx(fb, C::kStageBytes * kCG);
+            if constexpr (kCG == 2) fb = mapa_shared(fb, full_owner_rank);
+            const int k_idx = kb * kBlockK;
+            if (!a_mn) {
+              tma_load_2d<kCG>(tmA, fb, sA, k_idx, m_idx);  // box {64 k, 128 rows}
+            } else {
 #pragma unroll
-            for (int h = 0; h < kBlockM / 64; ++h)        // boxes {64 rows, 64 k}
-              tma_load_2d<kCG>(tmA, fb, sA + h * 8192, m_idx + 64 * h, k_idx);
-          }
-          if (!pr.b_mn) {
-            tma_load_2d<kCG>(tmB, fb, sB, k_idx, n_idx);  // box {64 k, kBRows rows}
-          } else {
+              for (int h = 0; h < kBlockM / 64; ++h)        // boxes {64 rows, 64 k}
+                tma_load_2d<kCG>(tmA, fb, sA + h * 8192, m_idx + 64 * h, k_idx);
+            }
+            if constexpr (kMC == 1) {
+              if (!b_mn) {
+                tma_load_2d<kCG>(tmB, fb, sB, k_idx, n_idx);  // box {64 k, kBRows rows}
+              } else {
 #pragma unroll
-            for (int h = 0; h < C::kBRows / 64; ++h)
-              tma_load_2d<kCG>(tmB, fb, sB + h * 8192, n_idx + 64 * h, k_idx);
+                for (int h = 0; h < C::kBRows / 64; ++h)
+                  tma_load_2d<kCG>(tmB, fb, sB + h * 8192, n_idx + 64 * h, k_idx);
+              }
+            } else {
+              // this CTA fetches 1/kMC of the common B tile and multicasts it to every CTA of the cluster
+              constexpr int kPart = C::kBRows / kMC;  // rows of B per CTA
+              if (!b_mn) {
+                tma_load_2d_mcast(tmB, fb, sB + mc_rank * (kPart * kBlockK * 2), k_idx, n_idx + mc_rank * kPart,
+                                  kMcMask);         // box {64 k, kPart rows}
+              } else {
+#pragma unroll
+                for (int h = 0; h < kPart / 64; ++h) {
+                  const int hh = mc_rank * (kPart / 64) + h;
+                  tma_load_2d_mcast(tmB, fb, sB + hh * 8192, n_idx + 64 * hh, k_idx, kMcMask);
+                }
+              }
+            }
           }
+          __syncwarp();
           if (++stage == C::kStages) {
             stage = 0;
             phase ^= 1u;
           }
         }
       }
+      if (p.wait_stats && lane == 0) p.wait_stats[8ll * blockIdx.x + 0] = static_cast<unsigned long long>(w_empty);
     }
-    __syncwarp();
   } else if (warp == kMmaWarp) {
     // ===================================== MMA issuer =====================================
-    if (cta_rank == 0 && lane == 0) {
+    // Warp-uniform loop; one elected lane issues tcgen05.mma / tcgen05.commit.
+    if (cta_rank == 0) {
       int stage = 0;
       uint32_t phase = 0;
       int as = 0;
       uint32_t aphase = 0;
+      long long w_full = 0, w_tmem = 0, w_issue = 0, w_commit = 0;
+      const bool prof = p.wait_stats != nullptr;
+      const long long c_start = clock_cycles();
       for (int t = cluster_id; t < total_tiles; t += num_clusters) {
-        const TileCoord tc = decode_tile(p, t);
+        const TileCoord tc = decode_tile<kMC>(p, t, mc_rank);
         const Problem& pr = p.prob[tc.prob];
         const uint32_t idesc = make_idesc_bf16(C::kTileM, kTileN, pr.a_mn, pr.b_mn);
         // K-major: 8-row groups 1024 B apart (SBO), K advance 32 B inside the swizzle row.
@@ -308,43 +417,71 @@ siglip_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_consta
         const uint32_t a_lbo = pr.a_mn ? 8192u : 16u, b_lbo = pr.b_mn ? 8192u : 16u;
         const uint32_t a_adv = pr.a_mn ? (kUmmaK * 128u) >> 4 : (kUmmaK * 2u) >> 4;
         const uint32_t b_adv = pr.b_mn ? (kUmmaK * 128u) >> 4 : (kUmmaK * 2u) >> 4;
+        // descriptors of stage 0; later stages add stage * kStageBytes >> 4 to the start-address field
+        const uint64_t adesc0 = make_smem_desc_sw128(smem_base, a_lbo, 1024u);
+        const uint64_t bdesc0 = make_smem_desc_sw128(smem_base + C::kABytes, b_lbo, 1024u);
         const int num_kb = (pr.K + kBlockK - 1) / kBlockK;
-        mbar_wait(tmem_empty_bar(as), aphase ^ 1u, p.dbg, 2, t, as);
+        mbar_wait(tmem_empty_bar(as), aphase ^ 1u, p.dbg, 2, t, as, 0, prof ? &w_tmem : nullptr);
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(as * kTileN);
         for (int kb = 0; kb < num_kb; ++kb) {
-          mbar_wait(full_bar(stage), phase, p.dbg, 3, t, kb);
+          mbar_wait(full_bar(stage), phase, p.dbg, 3, t, kb, 0, prof ? &w_full : nullptr);
           tc_fence_after();
-          const uint32_t sA = smem_base + stage * C::kStageBytes;
-          const uint32_t sB = sA + C::kABytes;
-          const uint64_t adesc = make_smem_desc_sw128(sA, a_lbo, 1024u);
-          const uint64_t bdesc = make_smem_desc_sw128(sB, b_lbo, 1024u);
+          const long long c0 = prof ? clock_cycles() : 0;
+          long long c1 = 0;
+          if (elect_one_sync()) {
+            const uint64_t adesc = adesc0 + static_cast<uint64_t>(stage * (C::kStageBytes >> 4));
+            const uint64_t bdesc = bdesc0 + static_cast<uint64_t>(stage * (C::kStageBytes >> 4));
 #pragma unroll
-          for (int k = 0; k < kBlockK / kUmmaK; ++k) {
-            umma_bf16<kCG>(tmem_d, adesc + static_cast<uint64_t>(k * a_adv), bdesc + static_cast<uint64_t>(k * b_adv),
-                           idesc, static_cast<uint32_t>((kb | k) != 0));
+            for (int k = 0; k < kBlockK / kUmmaK; ++k) {
+              umma_bf16<kCG>(tmem_d, adesc + static_cast<uint64_t>(k * a_adv),
+                             bdesc + static_cast<uint64_t>(k * b_adv), idesc, static_cast<uint32_t>((kb | k) != 0));
+            }
+            c1 = prof ? clock_cycles() : 0;
+            if constexpr (kMC > 1) {
+              umma_commit_mcast(empty_bar(stage), kMcMask);  // stage is free in every CTA that writes into it
+            } else {
+              umma_commit<kCG>(empty_bar(stage));  // frees the smem stage (both CTAs) when the MMAs retire
+            }
+            if (kb == num_kb - 1) umma_commit<kCG>(tmem_full_bar(as));  // accumulator ready (both CTAs)
+            if (prof) {
+              const long long c2 = clock_cycles();
+              w_issue += c1 - c0;
+              w_commit += c2 - c1;
+            }
           }
-          umma_commit<kCG>(empty_bar(stage));  // frees the smem stage (both CTAs) when the MMAs retire
+          __syncwarp();
           if (++stage == C::kStages) {
             stage = 0;
             phase ^= 1u;
           }
         }
-        umma_commit<kCG>(tmem_full_bar(as));   // accumulator ready for the epilogue (both CTAs)
         if (++as == kAccStages) {
           as = 0;
           aphase ^= 1u;
         }
       }
+      if (prof) {
+        // the elected lane accumulated issue/commit; every lane has the (identical) wait counters
+        const long long wi = __reduce_max_sync(0xffffffffu, static_cast<int>(w_issue >> 8));
+        const long long wc = __reduce_max_sync(0xffffffffu, static_cast<int>(w_commit >> 8));
+        if (lane == 0) {
+          p.wait_stats[8ll * blockIdx.x + 1] = static_cast<unsigned long long>(w_full);
+          p.wait_stats[8ll * blockIdx.x + 2] = static_cast<unsigned long long>(w_tmem);
+          p.wait_stats[8ll * blockIdx.x + 3] = static_cast<unsigned long long>(clock_cycles() - c_start);
+          p.wait_stats[8ll * blockIdx.x + 4] = static_cast<unsigned long long>(wi << 8);
+          p.wait_stats[8ll * blockIdx.x + 5] = static_cast<unsigned long long>(wc << 8);
+        }
+      }
     }
-    __syncwarp();
   } else if (warp < kNumEpiWarps) {
     // ===================================== epilogue =====================================
-    const int q = warp & 3;       // TMEM lane quarter this warp may touch
-    const int half = warp >> 2;   // which 128 columns of the 256-column accumulator
+    const int q = warp & 3;        // TMEM lane quarter this warp may touch
+    const int cgrp = warp >> 2;    // which kEpiCols columns of the 256-column accumulator
     const int row_in_cta = q * 32 + lane;
     const float t_exact = expf(*p.t_prime);
     const float bias = (kMode == kModeLoss) ? *p.bias : 0.f;
+    const float tl = t_exact * kLog2e, bl = bias * kLog2e;
     double d_sp = 0.0, d_g = 0.0, d_gs = 0.0;
     int as = 0;
     uint32_t aphase = 0;
@@ -354,25 +491,27 @@ siglip_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_consta
       empty_remote[a] = (kCG == 2) ? mapa_shared(tmem_empty_bar(a), 0) : tmem_empty_bar(a);
     }
     for (int t = cluster_id; t < total_tiles; t += num_clusters) {
-      const TileCoord tc = decode_tile(p, t);
+      const TileCoord tc = decode_tile<kMC>(p, t, mc_rank);
       const Problem& pr = p.prob[tc.prob];
       const int row = tc.m_blk * C::kTileM + static_cast<int>(cta_rank) * kBlockM + row_in_cta;
-      const int col_base = tc.n_blk * kTileN + half * 128;
-      mbar_wait(tmem_full_bar(as), aphase, p.dbg, 4, t, as);
+      const int col_base = tc.n_blk * kTileN + cgrp * kEpiCols;
+      mbar_wait(tmem_full_bar(as), aphase, p.dbg, 4, t, as, p.epi_sleep_ns);
       tc_fence_after();
-      const uint32_t taddr = tmem_base + static_cast<uint32_t>(as * kTileN + half * 128) +
+      const uint32_t taddr = tmem_base + static_cast<uint32_t>(as * kTileN + cgrp * kEpiCols) +
                              (static_cast<uint32_t>(q * 32) << 16);
-      uint32_t va[32], vb[32];
       float acc_sp = 0.f, acc_g = 0.f, acc_gs = 0.f;
 
       bool edge = false, diag = false;
-      __nv_bfloat16* g_row = nullptr;
+      GStore gst;
+      gst.tmap = &tmG;
+      gst.stage = staging_base + static_cast<uint32_t>(warp) * kStagingBytesPerWarp;
+      gst.row0 = tc.m_blk * C::kTileM + static_cast<int>(cta_rank) * kBlockM + q * 32;
+      gst.lane = lane;
       float scale = 0.f, fix = 0.f;
       if constexpr (kMode == kModeLoss) {
         const int tile_m0 = tc.m_blk * C::kTileM, tile_n0 = tc.n_blk * kTileN;
         edge = (tile_m0 + C::kTileM > pr.M) || (tile_n0 + kTileN > pr.N);
         diag = p.own_chunk && (tile_m0 < tile_n0 + kTileN) && (tile_n0 < tile_m0 + C::kTileM);
-        g_row = p.G + static_cast<long long>(row) * p.ldg;
       } else {
         scale = t_exact * p.inv_b;
         fix = (pr.fix_vec != nullptr && row < pr.M) ? pr.fix_vec[row] : 0.f;
@@ -382,45 +521,50 @@ siglip_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_consta
         const int col0 = col_base + c * 32;
         if constexpr (kMode == kModeLoss) {
           const bool sg = p.store_g != 0;
-          if (edge) {
-            if (diag)
-              loss_slab<true, true>(v, t_exact, bias, row, col0, pr.M, pr.N, sg, g_row, p.g_diag, acc_sp, acc_g, acc_gs);
+          if (!edge && !diag) {
+            // z is monotone in s (t > 0): the slab is "all very negative" iff max s is
+            float smax = __uint_as_float(v[0]);
+#pragma unroll
+            for (int j = 1; j < 32; ++j) smax = fmaxf(smax, __uint_as_float(v[j]));
+            const bool fast = __all_sync(0xffffffffu, fmaf(smax, t_exact, bias) < kFastZ);
+            if (fast)
+              loss_slab_fast(v, tl, bl, col0, sg, gst, acc_sp, acc_g, acc_gs);
             else
-              loss_slab<true, false>(v, t_exact, bias, row, col0, pr.M, pr.N, sg, g_row, p.g_diag, acc_sp, acc_g, acc_gs);
+              loss_slab<false, false>(v, t_exact, bias, row, col0, pr.M, pr.N, sg, gst, p.g_diag, acc_sp, acc_g, acc_gs);
+          } else if (edge) {
+            if (diag)
+              loss_slab<true, true>(v, t_exact, bias, row, col0, pr.M, pr.N, sg, gst, p.g_diag, acc_sp, acc_g, acc_gs);
+            else
+              loss_slab<true, false>(v, t_exact, bias, row, col0, pr.M, pr.N, sg, gst, p.g_diag, acc_sp, acc_g, acc_gs);
           } else {
-            if (diag)
-              loss_slab<false, true>(v, t_exact, bias, row, col0, pr.M, pr.N, sg, g_row, p.g_diag, acc_sp, acc_g, acc_gs);
-            else
-              loss_slab<false, false>(v, t_exact, bias, row, col0, pr.M, pr.N, sg, g_row, p.g_diag, acc_sp, acc_g, acc_gs);
+            loss_slab<false, true>(v, t_exact, bias, row, col0, pr.M, pr.N, sg, gst, p.g_diag, acc_sp, acc_g, acc_gs);
           }
         } else {
           out_slab(v, scale, row, col0, pr, fix);
         }
       };
 
-      // 4 slabs of 32 columns; the TMEM load of slab c+1 is in flight while slab c is processed.
-      tmem_ld_32x32(taddr + 0, va);
-      tmem_ld_wait();
-      tmem_ld_32x32(taddr + 32, vb);
-      slab(va, 0);
-      tmem_ld_wait();
-      tmem_ld_32x32(taddr + 64, va);
-      slab(vb, 1);
-      tmem_ld_wait();
-      tmem_ld_32x32(taddr + 96, vb);
-      slab(va, 2);
-      tmem_ld_wait();
-      // every TMEM read of this warp for this accumulator stage has landed: hand the stage back
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) {
-        if (kCG == 2 && cta_rank != 0) {
-          mbar_arrive_cluster(empty_remote[as]);
-        } else {
-          mbar_arrive(tmem_empty_bar(as));
+      // kSlabsPerWarp slabs of 32 columns. With four epilogue warps per SM sub-partition the TMEM load latency
+      // of one warp is covered by the arithmetic of the others.
+      uint32_t v[32];
+#pragma unroll
+      for (int c = 0; c < kSlabsPerWarp; ++c) {
+        tmem_ld_32x32(taddr + 32 * c, v);
+        tmem_ld_wait();
+        if (c == kSlabsPerWarp - 1) {
+          // every TMEM read of this warp for this accumulator stage has landed: hand the stage back
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) {
+            if (kCG == 2 && cta_rank != 0) {
+              mbar_arrive_cluster(empty_remote[as]);
+            } else {
+              mbar_arrive(tmem_empty_bar(as));
+            }
+          }
         }
+        slab(v, c);
       }
-      slab(vb, 3);
 
       if constexpr (kMode == kModeLoss) {
         d_sp += static_cast<double>(acc_sp);
@@ -433,7 +577,9 @@ siglip_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_consta
       }
     }
     if constexpr (kMode == kModeLoss) {
-      // fixed-order reduction: lanes -> warp -> 8 warps -> one slot per CTA (summed later in slot order)
+      // all sigma slabs of this warp must be in global memory before the kernel ends
+      if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+      // fixed-order reduction: lanes -> warp -> epilogue warps -> one slot per CTA (summed later in slot order)
       d_sp = warp_sum(d_sp);
       d_g = warp_sum(d_g);
       d_gs = warp_sum(d_gs);
@@ -512,8 +658,8 @@ siglip_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_consta
 
   // ===================================== teardown =====================================
   tc_fence_before();
-  if constexpr (kCG == 2) {
-    cluster_sync_all();
+  if constexpr (kClusterSize > 1) {
+    cluster_sync_all();   // peers may still multicast into this CTA's smem / arrive on its barriers
   } else {
     __syncthreads();
   }
@@ -603,18 +749,19 @@ __global__ void wait_flags_kernel(const volatile unsigned int* flags, int n, uns
   }
 }
 
-template <int kCG, int kMode>
+template <int kCG, int kMode, int kStages, int kMC>
 int launch_impl(const CUtensorMap* tmA0, const CUtensorMap* tmB0, const CUtensorMap* tmA1, const CUtensorMap* tmB1,
-                const KernelParams& p, int num_sms, cudaStream_t stream) {
-  using C = Cfg<kCG>;
-  auto kern = siglip_gemm_kernel<kCG, kMode>;
+                const CUtensorMap* tmG, const KernelParams& p, int num_sms, cudaStream_t stream) {
+  using C = Cfg<kCG, kMode, kStages>;
+  constexpr int kClusterSize = kCG * kMC;
+  auto kern = siglip_gemm_kernel<kCG, kMode, kStages, kMC>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes);
   if (e != cudaSuccess) return static_cast<int>(e);
-  const int total_tiles =
-      p.prob[0].tiles_m * p.prob[0].tiles_n + (p.nprob > 1 ? p.prob[1].tiles_m * p.prob[1].tiles_n : 0);
-  int grid = (num_sms / kCG) * kCG;
-  if (grid > total_tiles * kCG) grid = total_tiles * kCG;
-  if (grid < kCG) grid = kCG;
+  int total_tiles = ((p.prob[0].tiles_m + kMC - 1) / kMC) * p.prob[0].tiles_n;
+  if (p.nprob > 1) total_tiles += ((p.prob[1].tiles_m + kMC - 1) / kMC) * p.prob[1].tiles_n;
+  int grid = (num_sms / kClusterSize) * kClusterSize;
+  if (grid > total_tiles * kClusterSize) grid = total_tiles * kClusterSize;
+  if (grid < kClusterSize) grid = kClusterSize;
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(grid);
   cfg.blockDim = dim3(kNumThreads);
@@ -622,30 +769,99 @@ int launch_impl(const CUtensorMap* tmA0, const CUtensorMap* tmB0, const CUtensor
   cfg.stream = stream;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = kCG;
+  attr[0].val.clusterDim.x = kClusterSize;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  e = cudaLaunchKernelEx(&cfg, kern, *tmA0, *tmB0, *tmA1, *tmB1, p);
+  e = cudaLaunchKernelEx(&cfg, kern, *tmA0, *tmB0, *tmA1, *tmB1, *tmG, p);
   return static_cast<int>(e);
 }
 
 }  // namespace
 
-size_t gemm_smem_bytes(int cta_group) {
-  return cta_group == 2 ? static_cast<size_t>(Cfg<2>::kSmemBytes) : static_cast<size_t>(Cfg<1>::kSmemBytes);
+int query_max_active_clusters(int cta_group) {
+  int n = -1;
+  cudaLaunchConfig_t cfg{};
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cfg.blockDim = dim3(kNumThreads);
+  cfg.gridDim = dim3(148);
+  if (cta_group == 2) {
+    auto kern = siglip_gemm_kernel<2, kModeOut, 7, 1>;
+    cfg.dynamicSmemBytes = Cfg<2, kModeOut, 7>::kSmemBytes;
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, cfg.dynamicSmemBytes);
+    cudaOccupancyMaxActiveClusters(&n, kern, &cfg);
+  } else {
+    auto kern = siglip_gemm_kernel<1, kModeOut, 4, 2>;
+    cfg.dynamicSmemBytes = Cfg<1, kModeOut, 4>::kSmemBytes;
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, cfg.dynamicSmemBytes);
+    cudaOccupancyMaxActiveClusters(&n, kern, &cfg);
+  }
+  return n;
 }
 
-int launch_gemm(int cta_group, int mode, const CUtensorMap* tmA0, const CUtensorMap* tmB0, const CUtensorMap* tmA1,
-                const CUtensorMap* tmB1, const KernelParams& p, int num_sms, cudaStream_t stream) {
-  if (cta_group == 2) {
-    return mode == kModeLoss ? launch_impl<2, kModeLoss>(tmA0, tmB0, tmA1, tmB1, p, num_sms, stream)
-                             : launch_impl<2, kModeOut>(tmA0, tmB0, tmA1, tmB1, p, num_sms, stream);
-  }
-  return mode == kModeLoss ? launch_impl<1, kModeLoss>(tmA0, tmB0, tmA1, tmB1, p, num_sms, stream)
-                           : launch_impl<1, kModeOut>(tmA0, tmB0, tmA1, tmB1, p, num_sms, stream);
+int default_stages(int cta_group, int mode) {
+  if (mode == kModeLoss) return cta_group == 2 ? 6 : 4;
+  return cta_group == 2 ? 7 : 4;
 }
+
+size_t gemm_smem_bytes(int cta_group, int mode) {
+  if (mode == kModeLoss)
+    return cta_group == 2 ? static_cast<size_t>(Cfg<2, kModeLoss, 6>::kSmemBytes)
+                          : static_cast<size_t>(Cfg<1, kModeLoss, 4>::kSmemBytes);
+  return cta_group == 2 ? static_cast<size_t>(Cfg<2, kModeOut, 7>::kSmemBytes)
+                        : static_cast<size_t>(Cfg<1, kModeOut, 4>::kSmemBytes);
+}
+
+#define SIGLIP_LAUNCH(CG, MODE, ST, MC) \
+  return launch_impl<CG, MODE, ST, MC>(tmA0, tmB0, tmA1, tmB1, tmG, p, num_sms, stream)
+
+int launch_gemm(int cta_group, int mode, int stages, int mcast, const CUtensorMap* tmA0, const CUtensorMap* tmB0,
+                const CUtensorMap* tmA1, const CUtensorMap* tmB1, const CUtensorMap* tmG, const KernelParams& p,
+                int num_sms, cudaStream_t stream) {
+  if (stages <= 0) stages = default_stages(cta_group, mode);
+  if (cta_group == 2) {  // 2-CTA MMA pairs, no operand multicast
+    if (mode == kModeLoss) {
+      switch (stages) {
+        case 4: SIGLIP_LAUNCH(2, kModeLoss, 4, 1);
+        default: SIGLIP_LAUNCH(2, kModeLoss, 6, 1);
+      }
+    }
+    switch (stages) {
+      case 4: SIGLIP_LAUNCH(2, kModeOut, 4, 1);
+      default: SIGLIP_LAUNCH(2, kModeOut, 7, 1);
+    }
+  }
+  if (mcast == 2) {  // 1-CTA MMA, clusters of 2 sharing the B tile by TMA multicast
+    if (mode == kModeLoss) {
+      switch (stages) {
+        case 3: SIGLIP_LAUNCH(1, kModeLoss, 3, 2);
+        default: SIGLIP_LAUNCH(1, kModeLoss, 4, 2);
+      }
+    }
+    switch (stages) {
+      case 3: SIGLIP_LAUNCH(1, kModeOut, 3, 2);
+      default: SIGLIP_LAUNCH(1, kModeOut, 4, 2);
+    }
+  }
+  if (mode == kModeLoss) {
+    switch (stages) {
+      case 3: SIGLIP_LAUNCH(1, kModeLoss, 3, 1);
+      default: SIGLIP_LAUNCH(1, kModeLoss, 4, 1);
+    }
+  }
+  switch (stages) {
+    case 3: SIGLIP_LAUNCH(1, kModeOut, 3, 1);
+    default: SIGLIP_LAUNCH(1, kModeOut, 4, 1);
+  }
+}
+#undef SIGLIP_LAUNCH
 
 int launch_finalize(const double* partials, int nparts, const float* t_prime, float inv_b, float* loss,
                     float* dt_prime, float* dbias, cudaStream_t stream) {

@@ -42,6 +42,8 @@ struct KernelParams {
   double* partials;  // [gridDim.x][4] : sum softplus, sum g, sum g*s, (unused)
   int accumulate_partials;
   DebugRecord* dbg;
+  unsigned long long* wait_stats;  // optional [gridDim.x][4]: producer empty-wait, MMA full-wait, MMA tmem-wait, MMA loop cycles
+  unsigned int epi_sleep_ns;  // back-off of the epilogue warps while they wait for an accumulator (0 = spin)
   // optional NVSwitch peer pull performed by otherwise idle warps while the tiles compute:
   // copy `pull_bytes` from pull_src (peer GPU memory, P2P mapped) to pull_dst (local), both 16-B aligned.
   const uint4* pull_src;
@@ -54,12 +56,19 @@ struct KernelParams {
 
 enum KernelMode { kModeLoss = 0, kModeOut = 1 };
 
-// Dynamic shared memory needed by a configuration.
-size_t gemm_smem_bytes(int cta_group);
+// Dynamic shared memory needed by the default configuration of (cta_group, mode).
+size_t gemm_smem_bytes(int cta_group, int mode);
+int default_stages(int cta_group, int mode);
+int query_max_active_clusters(int cta_group);  // co-resident clusters of the out kernel (diagnostic)
 
-// Launch the warp-specialised persistent kernel. Returns cudaError_t as int.
-int launch_gemm(int cta_group, int mode, const CUtensorMap* tmA0, const CUtensorMap* tmB0, const CUtensorMap* tmA1,
-                const CUtensorMap* tmB1, const KernelParams& p, int num_sms, cudaStream_t stream);
+// Launch the warp-specialised persistent kernel. `stages` <= 0 selects the default pipeline depth.
+// tmG: store map of the sigma operand (loss mode; bf16 [B, B], box {32, 32}, 64B swizzle) — any valid map in out mode.
+// Returns cudaError_t as int.
+// mcast: 1 = every CTA loads its own operands; 2 (cta_group 1 only) = clusters of two CTAs on vertically adjacent
+// tiles share the B tile through TMA multicast (the K-major B map must then have box rows 128).
+int launch_gemm(int cta_group, int mode, int stages, int mcast, const CUtensorMap* tmA0, const CUtensorMap* tmB0,
+                const CUtensorMap* tmA1, const CUtensorMap* tmB1, const CUtensorMap* tmG, const KernelParams& p,
+                int num_sms, cudaStream_t stream);
 
 // loss = inv_b * S0 ; dbias = inv_b * S1 ; dt_prime = exp(t') * inv_b * S2  (S* = fixed-order sums of partials)
 int launch_finalize(const double* partials, int nparts, const float* t_prime, float inv_b, float* loss,

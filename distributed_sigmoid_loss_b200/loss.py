@@ -41,12 +41,12 @@ class SigmoidLossEngine:
     """Owns one ``siglip_ctx`` (workspaces + peer mappings) for a fixed (device, B, D, process group)."""
 
     def __init__(self, batch: int, dim: int, device: torch.device, group=None, cta_group: int = 2,
-                 overlap_pull: bool = True):
+                 overlap_pull: bool = True, rank_world: Optional[Tuple[int, int]] = None, loopback: bool = False):
         self._L = _capi.lib()
         if not torch.cuda.is_available() or self._L.siglip_device_count() == 0:
             raise RuntimeError("distributed_sigmoid_loss_b200 needs an sm_100 (B200) device; there is no CPU fallback")
         self.batch, self.dim, self.device, self.group = batch, dim, torch.device(device), group
-        self.rank, self.world = _group_rank_world(group)
+        self.rank, self.world = rank_world if rank_world is not None else _group_rank_world(group)
         h = ctypes.c_void_p()
         _capi.check(self._L.siglip_ctx_create(ctypes.byref(h), self.device.index or 0, self.rank, self.world,
                                               batch, dim))
@@ -54,7 +54,10 @@ class SigmoidLossEngine:
         _capi.check(self._L.siglip_ctx_set_option(h, _capi.SIGLIP_OPT_CTA_GROUP, int(cta_group)))
         _capi.check(self._L.siglip_ctx_set_option(h, _capi.SIGLIP_OPT_OVERLAP_PULL, int(bool(overlap_pull))))
         if self.world > 1:
-            self._exchange_handles()
+            if loopback:  # single-GPU test mode: one rank of a W-rank job, peers wired to local buffers
+                _capi.check(self._L.siglip_debug_loopback(h))
+            else:
+                self._exchange_handles()
 
     # -- peer bootstrap: replaces the reference's reliance on the process group for every step ------------
     def _exchange_handles(self) -> None:
@@ -69,6 +72,22 @@ class SigmoidLossEngine:
 
     def set_option(self, option: int, value: int) -> None:
         _capi.check(self._L.siglip_ctx_set_option(self._h, option, value))
+
+    def kernel_times(self):
+        """(loss_ms, loss_launches, grad_ms, grad_launches) since the last call; needs SIGLIP_OPT_KERNEL_TIMING."""
+        lm, gm = ctypes.c_double(), ctypes.c_double()
+        ln, gn = ctypes.c_int(), ctypes.c_int()
+        _capi.check(self._L.siglip_ctx_kernel_times(self._h, ctypes.byref(lm), ctypes.byref(ln), ctypes.byref(gm),
+                                                    ctypes.byref(gn)))
+        return lm.value, ln.value, gm.value, gn.value
+
+    def debug_set_text_chunk(self, chunk: int, txt: torch.Tensor) -> None:
+        _capi.check(self._L.siglip_debug_set_text_chunk(self._h, chunk, txt.data_ptr(), self._stream()))
+
+    def debug_get_slot(self, chunk: int) -> torch.Tensor:
+        out = torch.empty(self.batch, self.dim, device=self.device, dtype=torch.float32)
+        _capi.check(self._L.siglip_debug_get_slot(self._h, chunk, out.data_ptr(), self._stream()))
+        return out
 
     @property
     def workspace_bytes(self) -> int:

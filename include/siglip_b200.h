@@ -35,7 +35,11 @@ enum {
 /* tuning knobs (siglip_ctx_set_option) */
 enum {
   SIGLIP_OPT_CTA_GROUP = 1, /* 1: cta_group::1 128x256 tiles; 2: cta_group::2 256x256 tiles per SM pair (default) */
-  SIGLIP_OPT_OVERLAP_PULL = 2 /* 1 (default): pull the next text chunk inside the loss kernel; 0: separate copy kernel */
+  SIGLIP_OPT_OVERLAP_PULL = 2, /* 1 (default): pull the next text chunk inside the loss kernel; 0: separate copy */
+  SIGLIP_OPT_KERNEL_TIMING = 3, /* 1: bracket every loss / gradient kernel launch with CUDA events on the caller's stream */
+  SIGLIP_OPT_STAGES_LOSS = 4,  /* TMA->MMA pipeline depth of the loss kernel (0 = default) */
+  SIGLIP_OPT_STAGES_GRAD = 5,  /* ... of the gradient kernel */
+  SIGLIP_OPT_MCAST = 6         /* cta_group 1 only: 2 (default) = clusters of two CTAs share the B tile by TMA multicast */
 };
 
 /* Library / build identification: "siglip_b200 <version> sm_100a". */
@@ -96,6 +100,14 @@ int siglip_fwd_bwd_host(siglip_ctx* ctx, const void* img_host, const void* txt_h
                         float* loss_host, float* dimg_host, float* dtxt_host, float* dt_prime_host,
                         float* dbias_host, void* cuda_stream);
 
+/*
+ * With SIGLIP_OPT_KERNEL_TIMING on: device-synchronise, then return the summed CUDA-event durations (ms) and the
+ * launch counts of the loss kernel and of the gradient kernel since the previous call (for the roofline line
+ * of the benchmark). Resets the accumulation.
+ */
+int siglip_ctx_kernel_times(siglip_ctx* ctx, double* loss_ms, int* loss_launches, double* grad_ms,
+                            int* grad_launches);
+
 /* Kernels launched by the context since creation (for the benchmark's gpu_launches field). */
 unsigned long long siglip_ctx_launch_count(const siglip_ctx* ctx);
 
@@ -106,6 +118,22 @@ unsigned long long siglip_ctx_launch_count(const siglip_ctx* ctx);
  */
 int siglip_debug_gemm(int device, int cta_group, int M, int N, int K, const void* A, long long lda, int a_mn,
                       const void* Bm, long long ldb, int b_mn, float* C, long long ldc, void* cuda_stream);
+
+/* Same contraction launched `iters` times back to back (after one warm-up when iters > 1); *ms_per_iter receives
+ * the CUDA-event time per launch. Used to tune the mainloop apart from the loss epilogue. */
+int siglip_debug_gemm_timed(int device, int cta_group, int M, int N, int K, const void* A, long long lda, int a_mn,
+                            const void* Bm, long long ldb, int b_mn, float* C, long long ldc, int iters,
+                            float* ms_per_iter, void* cuda_stream);
+
+/*
+ * Test hooks for exercising the multi-chunk schedule of ONE rank on ONE GPU (world > 1 context, no peers):
+ * loopback wires every "peer" pointer to the context's own buffers; the test preloads the text chunks of the
+ * other ranks, runs siglip_fwd_bwd, and reads this rank's per-owner dtxt contributions back. The dtxt output of
+ * the step itself is meaningless in loopback mode (it sums the own slot world times).
+ */
+int siglip_debug_loopback(siglip_ctx* ctx);
+int siglip_debug_set_text_chunk(siglip_ctx* ctx, int chunk, const void* txt_dev, void* cuda_stream);
+int siglip_debug_get_slot(siglip_ctx* ctx, int chunk, float* out_dev, void* cuda_stream);
 
 void siglip_ctx_destroy(siglip_ctx* ctx);
 
