@@ -98,6 +98,13 @@ int encode_operand(CUtensorMap* m, const void* base, int rows, int K, long long 
 inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 inline int round_up(int a, int b) { return ceil_div(a, b) * b; }
 
+// The sigma operand G of the gradient contractions is stored as IEEE fp16 scaled by 2^14: 11 significant bits
+// (bf16 has 8; its 2^-9 rounding was the whole 1e-3 error budget when negatives dominate a gradient), and every
+// sigma down to 3.7e-9 (logit -19.4) stays a normal number. The out epilogue multiplies the accumulator by 2^-14.
+constexpr float kGScale = 16384.0f;
+// The embeddings enter the gradient contractions as fp16(x * 16): exact for every bf16 value with 3.8e-6 <= |x| <= 4094
+// (L2-normalised embeddings live in [~1e-4, 1]); the conversion runs inside the loss kernel's idle warps.
+constexpr float kXScale = 16.0f;
 constexpr int kMaxWorld = 32;
 constexpr int kFlagKinds = 3;  // 0: text ready, 1: dtxt slots ready, 2: step done
 
@@ -119,7 +126,9 @@ struct siglip_ctx {
   int cta_group = 2;
   int overlap_pull = 1;
   __nv_bfloat16* txt_all = nullptr;  // [world][B, D]; slot `rank` is what the peers pull
-  __nv_bfloat16* G = nullptr;        // [Bp, Bp] sigma operand of the current chunk
+  __nv_bfloat16* G = nullptr;        // [Bp, Bp] sigma operand of the current chunk (fp16 bits, scaled by kGScale)
+  __nv_bfloat16* img16 = nullptr;    // [B, D] fp16 copy (x kXScale) of the images, operand of the dtxt contraction
+  __nv_bfloat16* txt16 = nullptr;    // [B, D] fp16 copy (x kXScale) of the current text chunk, operand of dimg
   float* g_diag = nullptr;           // [B]
   float* slots = nullptr;            // [world][B, D] fp32 dtxt contributions, slot c is for owner c (world > 1)
   double* partials = nullptr;        // [num_sms][4]
@@ -177,8 +186,9 @@ int timing_mark(siglip_ctx* c, std::vector<cudaEvent_t>& evs, size_t& used, cuda
 
 // The loss kernel over one text chunk: S = img @ txt_c^T on tcgen05, fused scale/bias/log-sigmoid/reduce.
 int run_loss_chunk(siglip_ctx* c, const void* img, const __nv_bfloat16* txt_c, const float* t_prime,
-                   const float* bias, bool own, bool store_g, bool accumulate, const void* pull_src, void* pull_dst,
-                   size_t pull_bytes, const unsigned int* pull_flag, unsigned int pull_value, cudaStream_t st) {
+                   const float* bias, bool own, bool store_g, bool accumulate, bool convert_img,
+                   const void* pull_src, void* pull_dst, size_t pull_bytes, const unsigned int* pull_flag,
+                   unsigned int pull_value, cudaStream_t st) {
   const int cg = c->cta_group;
   const int tile_m = 128 * cg;
   CUtensorMap tmA, tmB;
@@ -202,6 +212,7 @@ int run_loss_chunk(siglip_ctx* c, const void* img, const __nv_bfloat16* txt_c, c
   p.g_diag = c->g_diag;
   p.own_chunk = own ? 1 : 0;
   p.store_g = store_g ? 1 : 0;
+  p.g_scale = kGScale;
   p.partials = c->partials;
   p.accumulate_partials = accumulate ? 1 : 0;
   p.dbg = c->dbg_dev;
@@ -210,6 +221,18 @@ int run_loss_chunk(siglip_ctx* c, const void* img, const __nv_bfloat16* txt_c, c
   p.pull_bytes = pull_bytes;
   p.pull_wait_flag = pull_flag;
   p.pull_wait_value = pull_value;
+  if (store_g) {  // training step: the gradient kernel of this chunk needs fp16 copies of its B operands
+    const unsigned long long n16 = static_cast<unsigned long long>(c->B) * c->D * sizeof(__nv_bfloat16) / 16;
+    p.cvt_scale = kXScale;
+    p.cvt_src[0] = reinterpret_cast<const uint4*>(txt_c);
+    p.cvt_dst[0] = reinterpret_cast<uint4*>(c->txt16);
+    p.cvt_n16[0] = n16;
+    if (convert_img) {
+      p.cvt_src[1] = reinterpret_cast<const uint4*>(img);
+      p.cvt_dst[1] = reinterpret_cast<uint4*>(c->img16);
+      p.cvt_n16[1] = n16;
+    }
+  }
   // store map of the sigma operand: [B, B] bf16 inside the padded [Bp, Bp] buffer, one 32x32 slab per TMA store
   CUtensorMap tmG;
   if ((rc = encode_bf16_2d(&tmG, c->G, (uint64_t)c->B, (uint64_t)c->B, (uint64_t)c->Bp, 32, 32,
@@ -233,9 +256,9 @@ int run_grad_chunk(siglip_ctx* c, const void* img, const __nv_bfloat16* txt_c, c
   CUtensorMap tmA0, tmB0, tmA1, tmB1;
   int rc;
   if ((rc = encode_operand(&tmA0, c->G, c->B, c->B, c->Bp, 0, 128))) return rc;
-  if ((rc = encode_operand(&tmB0, txt_c, c->D, c->B, c->D, 1, 0))) return rc;
+  if ((rc = encode_operand(&tmB0, c->txt16, c->D, c->B, c->D, 1, 0))) return rc;
   if ((rc = encode_operand(&tmA1, c->G, c->B, c->B, c->Bp, 1, 0))) return rc;
-  if ((rc = encode_operand(&tmB1, img, c->D, c->B, c->D, 1, 0))) return rc;
+  if ((rc = encode_operand(&tmB1, c->img16, c->D, c->B, c->D, 1, 0))) return rc;
   KernelParams p;
   memset(&p, 0, sizeof(p));
   p.nprob = 2;
@@ -247,6 +270,8 @@ int run_grad_chunk(siglip_ctx* c, const void* img, const __nv_bfloat16* txt_c, c
     pr.tiles_m = ceil_div(c->B, tile_m);
     pr.tiles_n = ceil_div(c->D, 256);
     pr.b_mn = 1;
+    pr.ab_f16 = 1;
+    pr.acc_scale = 1.0f / (kGScale * kXScale);
     pr.ldo = c->D;
     pr.ldx = c->D;
     pr.fix_vec = own ? c->g_diag : nullptr;
@@ -336,7 +361,7 @@ int step_impl(siglip_ctx* c, const void* img, const void* txt, const float* t_pr
       pull_src = pull_dst = nullptr;
       pull_flag = nullptr;
     }
-    if ((rc = run_loss_chunk(c, img, txt_c, t_prime, bias, k == 0, with_grad, true, pull_src, pull_dst, pull_bytes,
+    if ((rc = run_loss_chunk(c, img, txt_c, t_prime, bias, k == 0, with_grad, true, k == 0, pull_src, pull_dst, pull_bytes,
                              pull_flag, s, st)))
       return rc;
     if (with_grad) {
@@ -417,6 +442,8 @@ int siglip_ctx_create(siglip_ctx** out, int device, int rank, int world, int B, 
   };
   CK(alloc(reinterpret_cast<void**>(&c->G), static_cast<size_t>(c->Bp) * c->Bp * sizeof(__nv_bfloat16)));
   CK(alloc(reinterpret_cast<void**>(&c->g_diag), static_cast<size_t>(c->Bp) * sizeof(float)));
+  CK(alloc(reinterpret_cast<void**>(&c->img16), chunk_elems * sizeof(__nv_bfloat16)));
+  CK(alloc(reinterpret_cast<void**>(&c->txt16), chunk_elems * sizeof(__nv_bfloat16)));
   CK(alloc(reinterpret_cast<void**>(&c->partials), static_cast<size_t>(c->num_sms) * 4 * sizeof(double)));
   CK(alloc(reinterpret_cast<void**>(&c->flags), kFlagKinds * kMaxWorld * sizeof(unsigned int)));
   CK(alloc(reinterpret_cast<void**>(&c->scalars), 8 * sizeof(float)));
@@ -678,6 +705,8 @@ int siglip_debug_gemm_timed(int device, int cta_group, int M, int N, int K, cons
   p.prob[0].tiles_n = ceil_div(N, 256);
   p.prob[0].a_mn = a_mn ? 1 : 0;
   p.prob[0].b_mn = b_mn ? 1 : 0;
+  p.prob[0].ab_f16 = getenv("SIGLIP_DEBUG_AB_F16") ? 1 : 0;
+  p.prob[0].acc_scale = 1.0f;
   p.prob[0].out = C;
   p.prob[0].ldo = ldc;
   p.t_prime = zero;
@@ -765,6 +794,8 @@ void siglip_ctx_destroy(siglip_ctx* c) {
   cudaFree(c->txt_all);
   cudaFree(c->G);
   cudaFree(c->g_diag);
+  cudaFree(c->img16);
+  cudaFree(c->txt16);
   cudaFree(c->slots);
   cudaFree(c->partials);
   cudaFree(c->flags);

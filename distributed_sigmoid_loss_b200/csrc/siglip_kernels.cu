@@ -68,9 +68,15 @@ __device__ __forceinline__ float log1p_over_e(float e) {
   return p;
 }
 
-__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+// two fp32 -> one 32-bit word of two 16-bit floats (low half = lo). kF16: IEEE fp16, else bf16.
+template <bool kF16>
+__device__ __forceinline__ uint32_t pack_16x2(float lo, float hi) {
   uint32_t r;
-  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  if constexpr (kF16) {
+    asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  } else {
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  }
   return r;
 }
 
@@ -156,8 +162,10 @@ __device__ __forceinline__ void store_g_slab(const GStore& gs, int col0, const u
   }
 }
 
+template <bool kF16>
 __device__ __forceinline__ void loss_slab_fast(const uint32_t (&v)[32], float tl, float bl, int col0, bool store_g,
-                                               const GStore& gst, float& acc_sp, float& acc_g, float& acc_gs) {
+                                               const GStore& gst, float gscale, float& acc_sp, float& acc_g,
+                                               float& acc_gs) {
   uint32_t packed[16];
   float g_prev = 0.f;
 #pragma unroll
@@ -172,17 +180,17 @@ __device__ __forceinline__ void loss_slab_fast(const uint32_t (&v)[32], float tl
     acc_g += g;
     acc_gs = fmaf(g, s, acc_gs);
     if (j & 1) {
-      packed[j >> 1] = pack_bf16x2(g_prev, g);
+      packed[j >> 1] = pack_16x2<kF16>(g_prev, g * gscale);
     } else {
-      g_prev = g;
+      g_prev = g * gscale;
     }
   }
   if (store_g) store_g_slab(gst, col0, packed);
 }
 
-template <bool kEdge, bool kDiag>
+template <bool kEdge, bool kDiag, bool kF16>
 __device__ __forceinline__ void loss_slab(const uint32_t (&v)[32], float t, float b, int row, int col0, int nrows,
-                                          int ncols, bool store_g, const GStore& gst, float* g_diag,
+                                          int ncols, bool store_g, const GStore& gst, float gscale, float* g_diag,
                                           float& acc_sp, float& acc_g, float& acc_gs) {
   uint32_t packed[16];
   float g_prev = 0.f;
@@ -216,9 +224,9 @@ __device__ __forceinline__ void loss_slab(const uint32_t (&v)[32], float t, floa
     acc_g += g;
     acc_gs = fmaf(g, s, acc_gs);
     if (j & 1) {
-      packed[j >> 1] = pack_bf16x2(g_prev, g_store);
+      packed[j >> 1] = pack_16x2<kF16>(g_prev, g_store * gscale);
     } else {
-      g_prev = g_store;
+      g_prev = g_store * gscale;
     }
   }
   if (store_g) store_g_slab(gst, col0, packed);
@@ -227,6 +235,7 @@ __device__ __forceinline__ void loss_slab(const uint32_t (&v)[32], float t, floa
 // Epilogue of the out kernel: one 32-column slab.
 __device__ __forceinline__ void out_slab(const uint32_t (&v)[32], float scale, int row, int col0, const Problem& pr,
                                          float fix) {
+  const float as = pr.acc_scale;   // undoes the power-of-two scaling of an fp16 A operand (1 for bf16)
   if (row >= pr.M) return;
   float* orow = pr.out + static_cast<long long>(row) * pr.ldo;
   const __nv_bfloat16* xrow = pr.fix_mat ? pr.fix_mat + static_cast<long long>(row) * pr.ldx : nullptr;
@@ -235,10 +244,10 @@ __device__ __forceinline__ void out_slab(const uint32_t (&v)[32], float scale, i
     const int c = col0 + 4 * q;
     if (c < pr.N) {  // N % 4 == 0 is enforced by the host
       float4 o;
-      o.x = __uint_as_float(v[4 * q + 0]);
-      o.y = __uint_as_float(v[4 * q + 1]);
-      o.z = __uint_as_float(v[4 * q + 2]);
-      o.w = __uint_as_float(v[4 * q + 3]);
+      o.x = __uint_as_float(v[4 * q + 0]) * as;
+      o.y = __uint_as_float(v[4 * q + 1]) * as;
+      o.z = __uint_as_float(v[4 * q + 2]) * as;
+      o.w = __uint_as_float(v[4 * q + 3]) * as;
       if (xrow != nullptr) {
         const uint2 xb = *reinterpret_cast<const uint2*>(xrow + c);
         const float x0 = __uint_as_float(xb.x << 16), x1 = __uint_as_float(xb.x & 0xffff0000u);
@@ -411,7 +420,7 @@ siglip_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_consta
       for (int t = cluster_id; t < total_tiles; t += num_clusters) {
         const TileCoord tc = decode_tile<kMC>(p, t, mc_rank);
         const Problem& pr = p.prob[tc.prob];
-        const uint32_t idesc = make_idesc_bf16(C::kTileM, kTileN, pr.a_mn, pr.b_mn);
+        const uint32_t idesc = make_idesc_bf16(C::kTileM, kTileN, pr.a_mn, pr.b_mn, pr.ab_f16);
         // K-major: 8-row groups 1024 B apart (SBO), K advance 32 B inside the swizzle row.
         // MN-major: 64-element MN blocks 8192 B apart (LBO), 8-k groups 1024 B apart (SBO), K advance 16 rows.
         const uint32_t a_lbo = pr.a_mn ? 8192u : 16u, b_lbo = pr.b_mn ? 8192u : 16u;
@@ -528,16 +537,16 @@ siglip_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_consta
             for (int j = 1; j < 32; ++j) smax = fmaxf(smax, __uint_as_float(v[j]));
             const bool fast = __all_sync(0xffffffffu, fmaf(smax, t_exact, bias) < kFastZ);
             if (fast)
-              loss_slab_fast(v, tl, bl, col0, sg, gst, acc_sp, acc_g, acc_gs);
+              loss_slab_fast<true>(v, tl, bl, col0, sg, gst, p.g_scale, acc_sp, acc_g, acc_gs);
             else
-              loss_slab<false, false>(v, t_exact, bias, row, col0, pr.M, pr.N, sg, gst, p.g_diag, acc_sp, acc_g, acc_gs);
+              loss_slab<false, false, true>(v, t_exact, bias, row, col0, pr.M, pr.N, sg, gst, p.g_scale, p.g_diag, acc_sp, acc_g, acc_gs);
           } else if (edge) {
             if (diag)
-              loss_slab<true, true>(v, t_exact, bias, row, col0, pr.M, pr.N, sg, gst, p.g_diag, acc_sp, acc_g, acc_gs);
+              loss_slab<true, true, true>(v, t_exact, bias, row, col0, pr.M, pr.N, sg, gst, p.g_scale, p.g_diag, acc_sp, acc_g, acc_gs);
             else
-              loss_slab<true, false>(v, t_exact, bias, row, col0, pr.M, pr.N, sg, gst, p.g_diag, acc_sp, acc_g, acc_gs);
+              loss_slab<true, false, true>(v, t_exact, bias, row, col0, pr.M, pr.N, sg, gst, p.g_scale, p.g_diag, acc_sp, acc_g, acc_gs);
           } else {
-            loss_slab<false, true>(v, t_exact, bias, row, col0, pr.M, pr.N, sg, gst, p.g_diag, acc_sp, acc_g, acc_gs);
+            loss_slab<false, true, true>(v, t_exact, bias, row, col0, pr.M, pr.N, sg, gst, p.g_scale, p.g_diag, acc_sp, acc_g, acc_gs);
           }
         } else {
           out_slab(v, scale, row, col0, pr, fix);
@@ -653,6 +662,30 @@ siglip_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_consta
         p.pull_dst[i + 3ull * nthreads] = d;
       }
       for (; i < n16; i += nthreads) p.pull_dst[i] = p.pull_src[i];
+    }
+    // bf16 -> scaled fp16 copies of the embeddings for the gradient kernel (its sigma operand is fp16, and an
+    // MMA cannot mix fp16 with bf16): done here, off the critical path, while the tiles of this chunk compute.
+#pragma unroll 1
+    for (int job = 0; job < 2; ++job) {
+      const uint4* src = p.cvt_src[job];
+      uint4* dst = p.cvt_dst[job];
+      const unsigned long long n16 = p.cvt_n16[job];
+      if (src == nullptr || n16 == 0) continue;
+      const float sc = p.cvt_scale;
+      const unsigned long long nthreads = static_cast<unsigned long long>(gridDim.x) * 64ull;
+      for (unsigned long long i = static_cast<unsigned long long>(blockIdx.x) * 64ull + (threadIdx.x - kAllocWarp * 32);
+           i < n16; i += nthreads) {
+        const uint4 v = src[i];
+        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+        uint32_t o[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float lo = fminf(fmaxf(__uint_as_float(w[q] << 16) * sc, -65504.f), 65504.f);
+          const float hi = fminf(fmaxf(__uint_as_float(w[q] & 0xffff0000u) * sc, -65504.f), 65504.f);
+          o[q] = pack_16x2<true>(lo, hi);
+        }
+        dst[i] = make_uint4(o[0], o[1], o[2], o[3]);
+      }
     }
   }
 

@@ -17,6 +17,8 @@ struct Problem {
   int M, N, K;
   int tiles_m, tiles_n;
   int a_mn, b_mn;
+  int ab_f16;       // both operands are IEEE fp16 (gradient contractions: scaled sigma operand x scaled embeddings)
+  float acc_scale;  // multiplies the accumulator in the out epilogue (2^-k for a 2^k-scaled fp16 A operand)
   // epilogue of the "out" kernel: out = (beta ? out : 0) + scale * (acc + fix_vec[row] * fix_mat[row, col])
   float* out;
   long long ldo;
@@ -39,6 +41,7 @@ struct KernelParams {
   float* g_diag;   // [B] fp32: -sigma(-z_ii), the positive-pair term kept out of the bf16 operand
   int own_chunk;   // 1: this text chunk holds the positives of this rank's images
   int store_g;     // 0: forward only
+  float g_scale;   // sigma is stored as fp16(sigma * g_scale): 2^14 keeps sigma in (3.7e-9, 1) inside fp16's normal range
   double* partials;  // [gridDim.x][4] : sum softplus, sum g, sum g*s, (unused)
   int accumulate_partials;
   DebugRecord* dbg;
@@ -52,6 +55,11 @@ struct KernelParams {
   // flag the pull must see (>= pull_wait_value) before reading the peer buffer; null = no wait
   const volatile unsigned int* pull_wait_flag;
   unsigned int pull_wait_value;
+  // optional bf16 -> fp16 (x cvt_scale, clamped) conversions done by the same idle warps: [n16] 16-byte vectors each
+  const uint4* cvt_src[2];
+  uint4* cvt_dst[2];
+  unsigned long long cvt_n16[2];
+  float cvt_scale;
 };
 
 enum KernelMode { kModeLoss = 0, kModeOut = 1 };

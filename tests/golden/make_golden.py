@@ -46,7 +46,10 @@ def global_inputs(world: int, b: int, d: int):
     img = torch.randn(world * b, d)
     torch.manual_seed(40)
     txt = torch.randn(world * b, d)
-    return F.normalize(img), F.normalize(txt)
+    # L2-normalise (test_distributed_sigmoid_loss.py:99-101), then round to bf16-representable values and hand them to
+    # the reference as fp32: "the reference in fp32 on the same bf16-rounded inputs" is the parity yardstick
+    #  — the CUDA path consumes exactly these values as bf16.
+    return (F.normalize(img).to(torch.bfloat16).float(), F.normalize(txt).to(torch.bfloat16).float())
 
 
 def worker(rank: int, world: int, b: int, d: int, t_prime: float, bias: float, port: int, ret):
@@ -71,7 +74,7 @@ def worker(rank: int, world: int, b: int, d: int, t_prime: float, bias: float, p
         mod.bias.fill_(bias)
     loss = mod(img, txt)
     loss.backward()
-    out["ddp"] = dict(loss=float(loss), dimg=img.grad.numpy().copy(), dtxt=txt.grad.numpy().copy(),
+    out["ddp"] = dict(loss=float(loss.detach()), dimg=img.grad.numpy().copy(), dtxt=txt.grad.numpy().copy(),
                       dt_prime=float(mod.t_prime.grad), dbias=float(mod.bias.grad))
 
     # --- vendored open_clip variant, both ring flavours ---
@@ -83,7 +86,7 @@ def worker(rank: int, world: int, b: int, d: int, t_prime: float, bias: float, p
         loss = SigLipLoss(rank=rank, world_size=world, bidir=bidir)(img, txt, scale, lbias)
         loss.backward()
         out["rw_bidir" if bidir else "rw_uni"] = dict(
-            loss=float(loss), dimg=img.grad.numpy().copy(), dtxt=txt.grad.numpy().copy(),
+            loss=float(loss.detach()), dimg=img.grad.numpy().copy(), dtxt=txt.grad.numpy().copy(),
             dt_prime=float(scale.grad), dbias=float(lbias.grad))
     ret[rank] = out
     dist.barrier()

@@ -1,0 +1,107 @@
+"""CPU-side checks of the boundary: the C-ABI library loads, exports every symbol the header declares, fails
+loudly without a GPU, and the module mirror keeps the reference's surface. No compute calls (no GPU here)."""
+import ctypes
+import math
+import os
+import re
+
+import pytest
+import torch
+
+from distributed_sigmoid_loss_b200 import DDPSigmoidLoss, SigLipLoss, SigmoidLoss, _capi, chunk_schedule
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _header_symbols():
+    text = open(os.path.join(ROOT, "include", "siglip_b200.h")).read()
+    return sorted(set(re.findall(r"\b(siglip_[a-z_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    L = _capi.lib()
+    declared = _header_symbols()
+    assert declared, "no declarations parsed from include/siglip_b200.h"
+    for sym in declared:
+        assert hasattr(L, sym), f"{sym} declared in include/siglip_b200.h but not exported by {_capi.LIB_PATH}"
+    assert set(declared) == set(_capi.EXPORTED_SYMBOLS), set(declared) ^ set(_capi.EXPORTED_SYMBOLS)
+    assert "sm_100a" in _capi.version()
+
+
+def test_library_is_sm100a_native():
+    """The shipped binary contains tcgen05 / TMA machine code (SASS mnemonics), not a legacy mma.sync path."""
+    import shutil
+    import subprocess
+
+    if shutil.which("cuobjdump") is None:
+        pytest.skip("cuobjdump not on PATH")
+    sass = subprocess.run(["cuobjdump", "-sass", _capi.LIB_PATH], capture_output=True, text=True).stdout
+    assert "UTCHMMA" in sass and "UTMALDG" in sass and "LDTM" in sass and "UTMASTG" in sass
+    assert "HMMA.16816" not in sass
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")
+def test_no_device_fails_loudly():
+    L = _capi.lib()
+    assert L.siglip_device_count() == 0
+    h = ctypes.c_void_p()
+    rc = L.siglip_ctx_create(ctypes.byref(h), 0, 0, 1, 64, 64)
+    assert rc == _capi.SIGLIP_ERR_NO_DEVICE
+    assert "no CPU fallback" in _capi.last_error()
+    mod = DDPSigmoidLoss(4)
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        mod(torch.randn(4, 8), torch.randn(4, 8))
+
+
+def test_invalid_arguments_are_rejected_before_touching_the_gpu():
+    L = _capi.lib()
+    h = ctypes.c_void_p()
+    assert L.siglip_ctx_create(ctypes.byref(h), 0, 3, 2, 64, 64) == _capi.SIGLIP_ERR_INVALID   # rank >= world
+    assert L.siglip_ctx_create(ctypes.byref(h), 0, 0, 1, 64, 60) == _capi.SIGLIP_ERR_INVALID   # D % 8 != 0
+    assert L.siglip_ctx_create(ctypes.byref(h), 0, 0, 64, 64, 64) == _capi.SIGLIP_ERR_INVALID  # world > 32
+    assert L.siglip_ctx_handle_bytes() > 3 * 64
+
+
+def test_module_surface_matches_reference():
+    """Same parameters, dtypes, init values and state_dict keys as distributed_sigmoid_loss.py:9-15."""
+    mod = DDPSigmoidLoss(gpu_batch_size=8)
+    assert SigmoidLoss is DDPSigmoidLoss
+    sd = mod.state_dict()
+    assert list(sd.keys()) == ["t_prime", "bias"]
+    assert mod.t_prime.dtype == torch.float64 and mod.t_prime.dim() == 0
+    assert mod.bias.dtype == torch.float32 and mod.bias.dim() == 0
+    assert abs(float(mod.t_prime) - math.log(10)) < 1e-15 and float(mod.bias) == -10.0
+    assert mod.gpu_batch_size == 8
+    assert [n for n, _ in mod.named_parameters()] == ["t_prime", "bias"]
+    # the reference's checkpoints load unchanged
+    mod.load_state_dict({"t_prime": torch.tensor(1.5, dtype=torch.float64), "bias": torch.tensor(-3.0)})
+    assert float(mod.t_prime) == 1.5 and float(mod.bias) == -3.0
+
+
+def test_batch_mismatch_raises_runtime_error_like_reference():
+    mod = DDPSigmoidLoss(gpu_batch_size=8)
+    with pytest.raises(RuntimeError, match="must match the size"):
+        mod(torch.randn(4, 16), torch.randn(4, 16))
+    with pytest.raises(RuntimeError, match="same shape"):
+        mod(torch.randn(8, 16), torch.randn(6, 16))
+
+
+def test_siglip_adapter_signature():
+    m = SigLipLoss(cache_labels=False, rank=0, world_size=1, bidir=True, use_horovod=False)
+    assert (m.rank, m.world_size, m.bidir) == (0, 1, True)
+    with pytest.raises(AssertionError):
+        SigLipLoss(use_horovod=True)
+
+
+@pytest.mark.parametrize("world", [1, 2, 3, 4, 5, 8])
+def test_chunk_schedule_covers_every_pair_once(world):
+    """Every (image rank, text chunk) pair is scored exactly once; step 0 is the own chunk (positives); at every
+    step the W ranks read W distinct owners (a permutation: no NVSwitch hot spot)."""
+    seen = set()
+    for r in range(world):
+        sched = chunk_schedule(r, world)
+        assert sched[0] == r and sorted(sched) == list(range(world))
+        seen.update((r, c) for c in sched)
+    assert len(seen) == world * world
+    for k in range(world):
+        assert sorted(chunk_schedule(r, world)[k] for r in range(world)) == list(range(world))
