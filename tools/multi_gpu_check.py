@@ -1,0 +1,151 @@
+#!/usr/bin/env python
+"""Multi-GPU parity + timing check, one rank per GPU:
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29533 \
+        tools/multi_gpu_check.py [--time]
+
+Every rank builds the same seeded global batch, takes its slice, runs the module (NVSwitch peer pulls of the text
+chunks, per-owner dtxt slots, cross-rank reduction) and compares with
+  * the float64 closed form over the GLOBAL batch (oracle.closed_form) at a small shape, and
+  * fp32 autograd of the same math at a larger one (the text gradient reference is all-reduced over ranks).
+Exit code 0 only if every rank passes.
+"""
+from __future__ import annotations
+
+import argparse
+import math
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+import torch.distributed as dist  # noqa: E402
+
+
+def rel_f(a, b):
+    a, b = a.double(), b.double()
+    return float((a - b).norm() / (b.norm() + 1e-300))
+
+
+def main() -> int:
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--time", action="store_true")
+    ap.add_argument("--batch", type=int, default=16384)
+    ap.add_argument("--dim", type=int, default=1024)
+    ap.add_argument("--steps", type=int, default=10)
+    args = ap.parse_args()
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist.init_process_group("nccl", device_id=dev)
+    from distributed_sigmoid_loss_b200 import DDPSigmoidLoss, _capi
+    from oracle.siglip_oracle import closed_form, torch_reference_fp32
+
+    ok = True
+
+    def report(tag, errs, tol=1e-3):
+        nonlocal ok
+        good = all(v <= tol for v in errs.values())
+        ok &= good
+        print(f"[rank {rank}] {tag}: " + " ".join(f"{k}={v:.2e}" for k, v in errs.items()) + (" OK" if good else " FAIL"),
+              flush=True)
+
+    # ---- small: float64 closed form over the global batch -------------------------------------------------
+    for (B, D, tp, bias) in [(96, 64, math.log(10.0), -10.0), (512, 256, math.log(20.0), -5.0)]:
+        g = torch.Generator().manual_seed(99)
+        img_all = torch.nn.functional.normalize(torch.randn(world * B, D, generator=g)).to(torch.bfloat16)
+        txt_all = torch.nn.functional.normalize(torch.randn(world * B, D, generator=g)).to(torch.bfloat16)
+        ref = closed_form(img_all.float().numpy(), txt_all.float().numpy(), tp, bias, world)[rank]
+        mod = DDPSigmoidLoss(B).to(dev)
+        with torch.no_grad():
+            mod.t_prime.fill_(tp)
+            mod.bias.fill_(bias)
+        eng = mod.engine_for(B, D, dev)
+        img = img_all[rank * B:(rank + 1) * B].to(dev).contiguous()
+        txt = txt_all[rank * B:(rank + 1) * B].to(dev).contiguous()
+        for rep in range(2):   # second repetition exercises the step-to-step flag protocol
+            loss, dimg, dtxt, dtp, db = eng.fwd_bwd(img, txt, torch.tensor([tp], device=dev),
+                                                    torch.tensor([bias], device=dev))
+            loss_f = eng.fwd(img, txt, torch.tensor([tp], device=dev), torch.tensor([bias], device=dev))
+            torch.cuda.synchronize()
+            report(f"closed-form B={B} D={D} rep{rep}", dict(
+                loss=abs(float(loss) - ref["loss"]) / abs(ref["loss"]),
+                loss_fwd=abs(float(loss_f) - ref["loss"]) / abs(ref["loss"]),
+                dimg=rel_f(dimg.cpu(), torch.from_numpy(ref["dimg"])),
+                dtxt=rel_f(dtxt.cpu(), torch.from_numpy(ref["dtxt"])),
+                dtp=abs(float(dtp) - ref["dt_prime"]) / abs(ref["dt_prime"]),
+                db=abs(float(db) - ref["dbias"]) / abs(ref["dbias"])))
+        # module surface + overlap_pull off (separate copy) must agree too
+        eng.set_option(_capi.SIGLIP_OPT_OVERLAP_PULL, 0)
+        a, b = img.clone().requires_grad_(True), txt.clone().requires_grad_(True)
+        l2 = mod(a, b)
+        l2.backward()
+        torch.cuda.synchronize()
+        report(f"module/no-overlap B={B}", dict(
+            loss=abs(float(l2) - ref["loss"]) / abs(ref["loss"]),
+            dimg=rel_f(a.grad.float().cpu(), torch.from_numpy(ref["dimg"])),
+            dtxt=rel_f(b.grad.float().cpu(), torch.from_numpy(ref["dtxt"]))), tol=4e-3)
+        eng.set_option(_capi.SIGLIP_OPT_OVERLAP_PULL, 1)
+
+    # ---- larger: fp32 autograd; dtxt reference summed over ranks ------------------------------------------
+    B, D, tp, bias = 2048, 768, math.log(10.0), -10.0
+    g = torch.Generator().manual_seed(1234 + rank)
+    img = torch.nn.functional.normalize(torch.randn(B, D, generator=g)).to(torch.bfloat16).to(dev)
+    txt = torch.nn.functional.normalize(torch.randn(B, D, generator=g)).to(torch.bfloat16).to(dev)
+    chunks = [torch.empty_like(txt) for _ in range(world)]
+    dist.all_gather(chunks, txt)
+    ref = torch_reference_fp32(img, chunks, tp, bias, rank)
+    contrib = torch.stack(ref["dtxt_chunks"])             # [W, B, D] this rank's contributions
+    dist.all_reduce(contrib)                              # sum over ranks
+    mod = DDPSigmoidLoss(B).to(dev)
+    eng = mod.engine_for(B, D, dev)
+    loss, dimg, dtxt, dtp, db = eng.fwd_bwd(img, txt, torch.tensor([tp], device=dev), torch.tensor([bias], device=dev))
+    torch.cuda.synchronize()
+    report(f"fp32-autograd B={B} D={D}", dict(
+        loss=abs(float(loss) - ref["loss"]) / abs(ref["loss"]),
+        dimg=rel_f(dimg, ref["dimg"]), dtxt=rel_f(dtxt, contrib[rank]),
+        dtp=abs(float(dtp) - ref["dt_prime"]) / abs(ref["dt_prime"]),
+        db=abs(float(db) - ref["dbias"]) / abs(ref["dbias"])))
+
+    # ---- timing at the headline per-rank shape -------------------------------------------------------------
+    if args.time:
+        B, D = args.batch, args.dim
+        g = torch.Generator().manual_seed(1234 + rank)
+        img = torch.nn.functional.normalize(torch.randn(B, D, generator=g)).to(torch.bfloat16).to(dev)
+        txt = torch.nn.functional.normalize(torch.randn(B, D, generator=g)).to(torch.bfloat16).to(dev)
+        mod = DDPSigmoidLoss(B).to(dev)
+        eng = mod.engine_for(B, D, dev)
+        tpt, bt = torch.tensor([math.log(10.0)], device=dev), torch.tensor([-10.0], device=dev)
+        for overlap in (1, 0):
+            eng.set_option(_capi.SIGLIP_OPT_OVERLAP_PULL, overlap)
+            for _ in range(3):
+                eng.fwd_bwd(img, txt, tpt, bt)
+            dist.barrier()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(args.steps):
+                eng.fwd_bwd(img, txt, tpt, bt)
+            e1.record()
+            torch.cuda.synchronize()
+            t = torch.tensor([e0.elapsed_time(e1) / args.steps], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            if rank == 0:
+                ms = float(t)
+                print(f"[time W={world}] B={B} D={D} overlap_pull={overlap}: {ms:.3f} ms/step "
+                      f"{world * B / ms * 1e3 / 1e6:.2f} Mpairs/s (global) "
+                      f"{6.0 * B * world * B * D / ms / 1e9:.1f} TFLOP/s per GPU", flush=True)
+    flag = torch.tensor([0 if ok else 1], device=dev)
+    dist.all_reduce(flag)
+    dist.barrier()
+    dist.destroy_process_group()
+    if rank == 0:
+        print("MULTI-GPU CHECK", "PASS" if int(flag) == 0 else "FAIL", flush=True)
+    return 0 if int(flag) == 0 else 1
+
+
+if __name__ == "__main__":
+    sys.exit(main())
