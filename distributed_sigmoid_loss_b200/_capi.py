@@ -29,6 +29,7 @@ EXPORTED_SYMBOLS = (
     "siglip_fwd_bwd",
     "siglip_fwd",
     "siglip_fwd_bwd_host",
+    "siglip_scale",
     "siglip_ctx_kernel_times",
     "siglip_ctx_launch_count",
     "siglip_debug_gemm",
@@ -51,6 +52,7 @@ SIGLIP_OPT_KERNEL_TIMING = 3
 SIGLIP_OPT_STAGES_LOSS = 4
 SIGLIP_OPT_STAGES_GRAD = 5
 SIGLIP_OPT_MCAST = 6
+SIGLIP_OPT_GRAD_BF16 = 7
 
 _lib: Optional[ctypes.CDLL] = None
 
@@ -105,6 +107,8 @@ def lib() -> ctypes.CDLL:
     L.siglip_fwd.restype = ci
     L.siglip_fwd_bwd_host.argtypes = [vp, vp, vp, ctypes.c_float, ctypes.c_float, vp, vp, vp, vp, vp, vp]
     L.siglip_fwd_bwd_host.restype = ci
+    L.siglip_scale.argtypes = [vp, vp, vp, cs, ci, vp, vp]
+    L.siglip_scale.restype = ci
     L.siglip_ctx_kernel_times.argtypes = [vp, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ci),
                                           ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ci)]
     L.siglip_ctx_kernel_times.restype = ci

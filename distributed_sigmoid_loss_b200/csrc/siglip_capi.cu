@@ -150,6 +150,8 @@ struct siglip_ctx {
   int kernel_timing = 0;
   int stages_loss = 0, stages_grad = 0;  // 0 = kernel default
   int mcast = 2;                         // B-tile multicast cluster size for cta_group 1 (1 = off)
+  int grad_bf16 = 0;                     // dimg / dtxt outputs are bf16 instead of fp32
+  float* dimg_acc = nullptr;             // [B, D] fp32 running dimg over the chunks (world > 1)
   std::vector<cudaEvent_t> ev_loss, ev_grad;  // start, stop, start, stop, ...
   size_t ev_loss_used = 0, ev_grad_used = 0;
   bool loopback = false;
@@ -250,7 +252,8 @@ int run_loss_chunk(siglip_ctx* c, const void* img, const __nv_bfloat16* txt_c, c
 //   prob 0: dimg (+)= (t/B) * (G @ txt_c  [+ g_diag * txt_own])      A = G K-major,  B = txt_c N-major
 //   prob 1: dtxt_c  = (t/B) * (G^T @ img  [+ g_diag * img])          A = G M-major,  B = img N-major
 int run_grad_chunk(siglip_ctx* c, const void* img, const __nv_bfloat16* txt_c, const float* t_prime, bool own,
-                   bool beta_dimg, float* dimg, float* dtxt_out, cudaStream_t st) {
+                   const float* dimg_add, void* dimg_out, bool dimg_bf16, void* dtxt_out, bool dtxt_bf16,
+                   cudaStream_t st) {
   const int cg = c->cta_group;
   const int tile_m = 128 * cg;
   CUtensorMap tmA0, tmB0, tmA1, tmB1;
@@ -277,12 +280,14 @@ int run_grad_chunk(siglip_ctx* c, const void* img, const __nv_bfloat16* txt_c, c
     pr.fix_vec = own ? c->g_diag : nullptr;
   }
   p.prob[0].a_mn = 0;
-  p.prob[0].out = dimg;
-  p.prob[0].beta = beta_dimg ? 1 : 0;
+  p.prob[0].out = dimg_out;
+  p.prob[0].out_bf16 = dimg_bf16 ? 1 : 0;
+  p.prob[0].add_src = dimg_add;
+  p.prob[0].ld_add = c->D;
   p.prob[0].fix_mat = own ? txt_c : nullptr;
   p.prob[1].a_mn = 1;
   p.prob[1].out = dtxt_out;
-  p.prob[1].beta = 0;
+  p.prob[1].out_bf16 = dtxt_bf16 ? 1 : 0;
   p.prob[1].fix_mat = own ? reinterpret_cast<const __nv_bfloat16*>(img) : nullptr;
   p.t_prime = t_prime;
   p.inv_b = 1.0f / static_cast<float>(c->B);
@@ -308,7 +313,7 @@ int wait_peers(siglip_ctx* c, int kind, unsigned int value, cudaStream_t st) {
 }
 
 int step_impl(siglip_ctx* c, const void* img, const void* txt, const float* t_prime, const float* bias, float* loss,
-              float* dimg, float* dtxt, float* dt_prime, float* dbias, bool with_grad, cudaStream_t st) {
+              void* dimg, void* dtxt, float* dt_prime, float* dbias, bool with_grad, cudaStream_t st) {
   if (c == nullptr || img == nullptr || txt == nullptr || t_prime == nullptr || bias == nullptr || loss == nullptr)
     return fail(SIGLIP_ERR_INVALID, "null argument");
   if (with_grad && (dimg == nullptr || dtxt == nullptr || dt_prime == nullptr || dbias == nullptr))
@@ -365,8 +370,15 @@ int step_impl(siglip_ctx* c, const void* img, const void* txt, const float* t_pr
                              pull_flag, s, st)))
       return rc;
     if (with_grad) {
-      float* dtxt_out = (W == 1) ? dtxt : c->slots + cidx * chunk_elems;
-      if ((rc = run_grad_chunk(c, img, txt_c, t_prime, k == 0, k > 0, dimg, dtxt_out, st))) return rc;
+      // dimg accumulates over the chunks in an fp32 workspace; the last chunk writes the caller's buffer (fp32 or
+      // bf16). dtxt goes to the caller directly when there is one rank, else to this rank's slot for the owner.
+      const bool last = (k == W - 1);
+      const float* dimg_add = (k > 0) ? c->dimg_acc : nullptr;
+      void* dimg_out = last ? dimg : static_cast<void*>(c->dimg_acc);
+      void* dtxt_out = (W == 1) ? dtxt : static_cast<void*>(c->slots + cidx * chunk_elems);
+      if ((rc = run_grad_chunk(c, img, txt_c, t_prime, k == 0, dimg_add, dimg_out, last && c->grad_bf16, dtxt_out,
+                               W == 1 && c->grad_bf16, st)))
+        return rc;
     }
   }
   CKI(siglip::launch_finalize(c->partials, c->num_sms, t_prime, 1.0f / static_cast<float>(c->B), loss,
@@ -379,7 +391,7 @@ int step_impl(siglip_ctx* c, const void* img, const void* txt, const float* t_pr
       // (reduce-scatter SUM, torch functional.py:343-354) or the reverse ring (distributed_utils.py:75-77) delivers.
       if ((rc = signal_peers(c, 1, s, st))) return rc;
       if ((rc = wait_peers(c, 1, s, st))) return rc;
-      CKI(siglip::launch_reduce_slots(dtxt, c->reduce_ptrs_dev, W, chunk_elems, c->num_sms, st));
+      CKI(siglip::launch_reduce_slots(dtxt, c->grad_bf16, c->reduce_ptrs_dev, W, chunk_elems, c->num_sms, st));
       c->launches++;
     }
     if ((rc = signal_peers(c, 2, s, st))) return rc;
@@ -454,6 +466,7 @@ int siglip_ctx_create(siglip_ctx** out, int device, int rank, int world, int B, 
   if (world > 1) {
     CK(alloc(reinterpret_cast<void**>(&c->txt_all), chunk_elems * world * sizeof(__nv_bfloat16)));
     CK(alloc(reinterpret_cast<void**>(&c->slots), chunk_elems * world * sizeof(float)));
+    CK(alloc(reinterpret_cast<void**>(&c->dimg_acc), chunk_elems * sizeof(float)));
     CK(alloc(reinterpret_cast<void**>(&c->reduce_ptrs_dev), world * sizeof(float*)));
     CK(alloc(reinterpret_cast<void**>(&c->signal_ptrs_dev), kFlagKinds * world * sizeof(unsigned int*)));
   }
@@ -478,6 +491,9 @@ int siglip_ctx_set_option(siglip_ctx* c, int option, int value) {
       return 0;
     case SIGLIP_OPT_OVERLAP_PULL:
       c->overlap_pull = value ? 1 : 0;
+      return 0;
+    case SIGLIP_OPT_GRAD_BF16:
+      c->grad_bf16 = value ? 1 : 0;
       return 0;
     case SIGLIP_OPT_MCAST:
       if (value != 1 && value != 2) return fail(SIGLIP_ERR_INVALID, "mcast must be 1 or 2");
@@ -554,7 +570,7 @@ int siglip_ctx_import_handles(siglip_ctx* c, const void* all_ranks_bytes, size_t
 }
 
 int siglip_fwd_bwd(siglip_ctx* c, const void* img, const void* txt, const float* t_prime, const float* bias,
-                   float* loss, float* dimg, float* dtxt, float* dt_prime, float* dbias, void* cuda_stream) {
+                   float* loss, void* dimg, void* dtxt, float* dt_prime, float* dbias, void* cuda_stream) {
   return step_impl(c, img, txt, t_prime, bias, loss, dimg, dtxt, dt_prime, dbias, true,
                    static_cast<cudaStream_t>(cuda_stream));
 }
@@ -584,8 +600,11 @@ int siglip_fwd_bwd_host(siglip_ctx* c, const void* img_host, const void* txt_hos
   CK(cudaMemcpyAsync(c->scalars, sc, sizeof(sc), cudaMemcpyHostToDevice, st));
   CK(cudaMemcpyAsync(c->h_img, img_host, chunk_elems * sizeof(__nv_bfloat16), cudaMemcpyHostToDevice, st));
   CK(cudaMemcpyAsync(c->h_txt, txt_host, chunk_elems * sizeof(__nv_bfloat16), cudaMemcpyHostToDevice, st));
+  const int saved_bf16 = c->grad_bf16;
+  c->grad_bf16 = 0;  // the host entry returns fp32 gradients
   int rc = step_impl(c, c->h_img, c->h_txt, c->scalars + 0, c->scalars + 1, c->scalars + 2, c->h_dimg, c->h_dtxt,
                      c->scalars + 3, c->scalars + 4, true, st);
+  c->grad_bf16 = saved_bf16;
   if (rc) return rc;
   float res[3];
   CK(cudaMemcpyAsync(res, c->scalars + 2, sizeof(res), cudaMemcpyDeviceToHost, st));
@@ -659,6 +678,17 @@ int siglip_debug_get_slot(siglip_ctx* c, int chunk, float* out_dev, void* cuda_s
   const size_t chunk_elems = static_cast<size_t>(c->B) * c->D;
   CK(cudaMemcpyAsync(out_dev, c->slots + chunk * chunk_elems, chunk_elems * sizeof(float), cudaMemcpyDeviceToDevice,
                      static_cast<cudaStream_t>(cuda_stream)));
+  return 0;
+}
+
+int siglip_scale(siglip_ctx* c, const void* src, void* dst, size_t nbytes, int is_bf16, const float* g,
+                 void* cuda_stream) {
+  if (c == nullptr || src == nullptr || dst == nullptr || g == nullptr) return fail(SIGLIP_ERR_INVALID, "null argument");
+  if ((nbytes % 16) != 0 || (reinterpret_cast<uintptr_t>(src) & 15u) || (reinterpret_cast<uintptr_t>(dst) & 15u))
+    return fail(SIGLIP_ERR_INVALID, "siglip_scale needs 16-byte aligned buffers and a multiple of 16 bytes");
+  CK(cudaSetDevice(c->device));
+  CKI(siglip::launch_scale(src, dst, is_bf16, g, nbytes, c->num_sms, static_cast<cudaStream_t>(cuda_stream)));
+  c->launches++;
   return 0;
 }
 
@@ -797,6 +827,7 @@ void siglip_ctx_destroy(siglip_ctx* c) {
   cudaFree(c->img16);
   cudaFree(c->txt16);
   cudaFree(c->slots);
+  cudaFree(c->dimg_acc);
   cudaFree(c->partials);
   cudaFree(c->flags);
   cudaFree(c->scalars);

@@ -233,43 +233,47 @@ __device__ __forceinline__ void loss_slab(const uint32_t (&v)[32], float t, floa
 }
 
 // Epilogue of the out kernel: one 32-column slab.
+//   val = scale * (acc * acc_scale + fix * x[row, col]) (+ add_src[row, col]);  written as fp32 or bf16
 __device__ __forceinline__ void out_slab(const uint32_t (&v)[32], float scale, int row, int col0, const Problem& pr,
                                          float fix) {
-  const float as = pr.acc_scale;   // undoes the power-of-two scaling of an fp16 A operand (1 for bf16)
   if (row >= pr.M) return;
-  float* orow = pr.out + static_cast<long long>(row) * pr.ldo;
+  const float as = pr.acc_scale;   // undoes the power-of-two scaling of the fp16 operands (1 for bf16)
   const __nv_bfloat16* xrow = pr.fix_mat ? pr.fix_mat + static_cast<long long>(row) * pr.ldx : nullptr;
+  const float* arow = pr.add_src ? pr.add_src + static_cast<long long>(row) * pr.ld_add : nullptr;
 #pragma unroll
-  for (int q = 0; q < 8; ++q) {
-    const int c = col0 + 4 * q;
-    if (c < pr.N) {  // N % 4 == 0 is enforced by the host
-      float4 o;
-      o.x = __uint_as_float(v[4 * q + 0]) * as;
-      o.y = __uint_as_float(v[4 * q + 1]) * as;
-      o.z = __uint_as_float(v[4 * q + 2]) * as;
-      o.w = __uint_as_float(v[4 * q + 3]) * as;
+  for (int q = 0; q < 4; ++q) {       // 8 columns at a time (N % 8 == 0 is enforced by the host)
+    const int c = col0 + 8 * q;
+    if (c < pr.N) {
+      float o[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) o[e] = __uint_as_float(v[8 * q + e]) * as;
       if (xrow != nullptr) {
-        const uint2 xb = *reinterpret_cast<const uint2*>(xrow + c);
-        const float x0 = __uint_as_float(xb.x << 16), x1 = __uint_as_float(xb.x & 0xffff0000u);
-        const float x2 = __uint_as_float(xb.y << 16), x3 = __uint_as_float(xb.y & 0xffff0000u);
-        o.x = fmaf(fix, x0, o.x);
-        o.y = fmaf(fix, x1, o.y);
-        o.z = fmaf(fix, x2, o.z);
-        o.w = fmaf(fix, x3, o.w);
+        const uint4 xb = *reinterpret_cast<const uint4*>(xrow + c);
+        const uint32_t xw[4] = {xb.x, xb.y, xb.z, xb.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          o[2 * e + 0] = fmaf(fix, __uint_as_float(xw[e] << 16), o[2 * e + 0]);
+          o[2 * e + 1] = fmaf(fix, __uint_as_float(xw[e] & 0xffff0000u), o[2 * e + 1]);
+        }
       }
-      o.x *= scale;
-      o.y *= scale;
-      o.z *= scale;
-      o.w *= scale;
-      float4* dst = reinterpret_cast<float4*>(orow + c);
-      if (pr.beta) {
-        const float4 old = *dst;
-        o.x += old.x;
-        o.y += old.y;
-        o.z += old.z;
-        o.w += old.w;
+#pragma unroll
+      for (int e = 0; e < 8; ++e) o[e] *= scale;
+      if (arow != nullptr) {
+        const float4 a0 = *reinterpret_cast<const float4*>(arow + c);
+        const float4 a1 = *reinterpret_cast<const float4*>(arow + c + 4);
+        o[0] += a0.x; o[1] += a0.y; o[2] += a0.z; o[3] += a0.w;
+        o[4] += a1.x; o[5] += a1.y; o[6] += a1.z; o[7] += a1.w;
       }
-      *dst = o;
+      if (pr.out_bf16) {
+        __nv_bfloat16* orow = reinterpret_cast<__nv_bfloat16*>(pr.out) + static_cast<long long>(row) * pr.ldo;
+        *reinterpret_cast<uint4*>(orow + c) =
+            make_uint4(pack_16x2<false>(o[0], o[1]), pack_16x2<false>(o[2], o[3]), pack_16x2<false>(o[4], o[5]),
+                       pack_16x2<false>(o[6], o[7]));
+      } else {
+        float* orow = reinterpret_cast<float*>(pr.out) + static_cast<long long>(row) * pr.ldo;
+        *reinterpret_cast<float4*>(orow + c) = make_float4(o[0], o[1], o[2], o[3]);
+        *reinterpret_cast<float4*>(orow + c + 4) = make_float4(o[4], o[5], o[6], o[7]);
+      }
     }
   }
 }
@@ -730,8 +734,8 @@ __global__ void zero_partials_kernel(double* partials, int n) {
   if (i < n) partials[i] = 0.0;
 }
 
-__global__ void reduce_slots_kernel(float* __restrict__ out, const float* const* __restrict__ slots, int nslots,
-                                    size_t n4) {
+__global__ void reduce_slots_kernel(void* __restrict__ out, int out_bf16, const float* const* __restrict__ slots,
+                                    int nslots, size_t n4) {
   const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
   for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n4; i += stride) {
     float4 acc = reinterpret_cast<const float4*>(slots[0])[i];
@@ -742,7 +746,34 @@ __global__ void reduce_slots_kernel(float* __restrict__ out, const float* const*
       acc.z += v.z;
       acc.w += v.w;
     }
-    reinterpret_cast<float4*>(out)[i] = acc;
+    if (out_bf16) {
+      reinterpret_cast<uint2*>(out)[i] = make_uint2(pack_16x2<false>(acc.x, acc.y), pack_16x2<false>(acc.z, acc.w));
+    } else {
+      reinterpret_cast<float4*>(out)[i] = acc;
+    }
+  }
+}
+
+// dst = src * (*g): the whole backward() of the module (the gradients were produced for an upstream gradient of 1)
+__global__ void scale_kernel(const void* __restrict__ src, void* __restrict__ dst, int is_bf16,
+                             const float* __restrict__ g, size_t nvec) {
+  const float s = *g;
+  const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
+  for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < nvec; i += stride) {
+    const uint4 v = reinterpret_cast<const uint4*>(src)[i];
+    uint4 o;
+    if (is_bf16) {
+      const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+      uint32_t r[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+        r[q] = pack_16x2<false>(__uint_as_float(w[q] << 16) * s, __uint_as_float(w[q] & 0xffff0000u) * s);
+      o = make_uint4(r[0], r[1], r[2], r[3]);
+    } else {
+      o = make_uint4(__float_as_uint(__uint_as_float(v.x) * s), __float_as_uint(__uint_as_float(v.y) * s),
+                     __float_as_uint(__uint_as_float(v.z) * s), __float_as_uint(__uint_as_float(v.w) * s));
+    }
+    reinterpret_cast<uint4*>(dst)[i] = o;
   }
 }
 
@@ -908,9 +939,15 @@ int launch_zero_partials(double* partials, int nparts, cudaStream_t stream) {
   return static_cast<int>(cudaGetLastError());
 }
 
-int launch_reduce_slots(float* out, const float* const* slots_dev, int nslots, size_t n, int num_sms,
+int launch_reduce_slots(void* out, int out_bf16, const float* const* slots_dev, int nslots, size_t n, int num_sms,
                         cudaStream_t stream) {
-  reduce_slots_kernel<<<num_sms * 4, 256, 0, stream>>>(out, slots_dev, nslots, n / 4);
+  reduce_slots_kernel<<<num_sms * 4, 256, 0, stream>>>(out, out_bf16, slots_dev, nslots, n / 4);
+  return static_cast<int>(cudaGetLastError());
+}
+
+int launch_scale(const void* src, void* dst, int is_bf16, const float* g, size_t nbytes, int num_sms,
+                 cudaStream_t stream) {
+  scale_kernel<<<num_sms * 4, 256, 0, stream>>>(src, dst, is_bf16, g, nbytes / 16);
   return static_cast<int>(cudaGetLastError());
 }
 

@@ -19,13 +19,16 @@ struct Problem {
   int a_mn, b_mn;
   int ab_f16;       // both operands are IEEE fp16 (gradient contractions: scaled sigma operand x scaled embeddings)
   float acc_scale;  // multiplies the accumulator in the out epilogue (2^-k for a 2^k-scaled fp16 A operand)
-  // epilogue of the "out" kernel: out = (beta ? out : 0) + scale * (acc + fix_vec[row] * fix_mat[row, col])
-  float* out;
+  // epilogue of the "out" kernel:
+  //   out = scale * (acc * acc_scale + fix_vec[row] * fix_mat[row, col]) (+ add_src[row, col]); fp32 or bf16 output
+  void* out;
   long long ldo;
+  int out_bf16;
   const float* fix_vec;
   const __nv_bfloat16* fix_mat;
   long long ldx;
-  int beta;
+  const float* add_src;   // optional fp32 term (running dimg of the previous chunks)
+  long long ld_add;
 };
 
 struct KernelParams {
@@ -85,8 +88,12 @@ int launch_finalize(const double* partials, int nparts, const float* t_prime, fl
 int launch_zero_partials(double* partials, int nparts, cudaStream_t stream);
 
 // dtxt[j, d] = sum_r slots[r][j, d]   (slots may be peer-mapped pointers; fp32; n = elements)
-int launch_reduce_slots(float* out, const float* const* slots_dev, int nslots, size_t n, int num_sms,
+int launch_reduce_slots(void* out, int out_bf16, const float* const* slots_dev, int nslots, size_t n, int num_sms,
                         cudaStream_t stream);
+
+// dst = src * (*g) over nbytes (multiple of 16) of fp32 or bf16 data
+int launch_scale(const void* src, void* dst, int is_bf16, const float* g, size_t nbytes, int num_sms,
+                 cudaStream_t stream);
 
 // cross-rank flag helpers (peer-mapped pointers)
 int launch_signal_flags(unsigned int* const* flag_ptrs_dev, int n, unsigned int value, cudaStream_t stream);

@@ -100,21 +100,41 @@ class SigmoidLossEngine:
     def _stream(self) -> int:
         return torch.cuda.current_stream(self.device).cuda_stream
 
-    def fwd_bwd(self, img: torch.Tensor, txt: torch.Tensor, t_prime: torch.Tensor, bias: torch.Tensor):
-        """img/txt: [B, D] bf16 contiguous on self.device; t_prime/bias: fp32 [1]. Returns fp32 tensors
-        (loss[1], dimg[B,D], dtxt[B,D], dt_prime[1], dbias[1]) for an upstream gradient of 1."""
+    def fwd_bwd(self, img: torch.Tensor, txt: torch.Tensor, t_prime: torch.Tensor, bias: torch.Tensor,
+                grad_dtype: torch.dtype = torch.float32):
+        """img/txt: [B, D] bf16 contiguous on self.device; t_prime/bias: fp32 [1]. Returns
+        (loss[1], dimg[B,D], dtxt[B,D], dt_prime[1], dbias[1]) for an upstream gradient of 1; scalars are fp32,
+        dimg/dtxt are `grad_dtype` (fp32, or bf16 written directly by the kernel epilogue)."""
         self._check(img, txt)
+        if grad_dtype not in (torch.float32, torch.bfloat16):
+            raise RuntimeError("grad_dtype must be float32 or bfloat16")
+        want_bf16 = grad_dtype == torch.bfloat16
+        if want_bf16 != getattr(self, "_grad_bf16", False):
+            _capi.check(self._L.siglip_ctx_set_option(self._h, _capi.SIGLIP_OPT_GRAD_BF16, int(want_bf16)))
+            self._grad_bf16 = want_bf16
         opts = dict(device=self.device, dtype=torch.float32)
-        loss = torch.empty(1, **opts)
-        dimg = torch.empty(self.batch, self.dim, **opts)
-        dtxt = torch.empty(self.batch, self.dim, **opts)
-        dtp = torch.empty(1, **opts)
-        db = torch.empty(1, **opts)
+        scal = torch.empty(3, **opts)                 # loss, dt', dbias in one allocation
+        loss, dtp, db = scal[0:1], scal[1:2], scal[2:3]
+        dimg = torch.empty(self.batch, self.dim, device=self.device, dtype=grad_dtype)
+        dtxt = torch.empty(self.batch, self.dim, device=self.device, dtype=grad_dtype)
         with torch.cuda.device(self.device):
             _capi.check(self._L.siglip_fwd_bwd(self._h, img.data_ptr(), txt.data_ptr(), t_prime.data_ptr(),
                                                bias.data_ptr(), loss.data_ptr(), dimg.data_ptr(), dtxt.data_ptr(),
                                                dtp.data_ptr(), db.data_ptr(), self._stream()))
         return loss, dimg, dtxt, dtp, db
+
+    def scale(self, src: torch.Tensor, g: torch.Tensor) -> torch.Tensor:
+        """src * g with g a 1-element fp32 device tensor (grad_output): one fused pass of the C library."""
+        if src.dtype not in (torch.float32, torch.bfloat16) or not src.is_contiguous():
+            return src * g.to(src.dtype)
+        nbytes = src.numel() * src.element_size()
+        if nbytes % 16 != 0:
+            return src * g.to(src.dtype)
+        dst = torch.empty_like(src)
+        with torch.cuda.device(self.device):
+            _capi.check(self._L.siglip_scale(self._h, src.data_ptr(), dst.data_ptr(), nbytes,
+                                             int(src.dtype == torch.bfloat16), g.data_ptr(), self._stream()))
+        return dst
 
     def fwd(self, img: torch.Tensor, txt: torch.Tensor, t_prime: torch.Tensor, bias: torch.Tensor) -> torch.Tensor:
         self._check(img, txt)
@@ -176,8 +196,11 @@ class _SigmoidLossFn(torch.autograd.Function):
         ctx.in_meta = (img.dtype, txt.dtype, t_prime.dtype, bias.dtype, t_prime.shape, bias.shape,
                        t_prime.device, bias.device)
         if need_grad:
-            loss, dimg, dtxt, dtp, db = engine.fwd_bwd(img_b, txt_b, tp, b)
+            # gradients in the dtype autograd would return for these inputs: bf16 straight from the kernel epilogue
+            gdt = torch.bfloat16 if (img.dtype == torch.bfloat16 and txt.dtype == torch.bfloat16) else torch.float32
+            loss, dimg, dtxt, dtp, db = engine.fwd_bwd(img_b, txt_b, tp, b, gdt)
             ctx.save_for_backward(dimg, dtxt, dtp, db)
+            ctx.engine = engine
         else:
             loss = engine.fwd(img_b, txt_b, tp, b)
         # reference result dtype: promote(input dtype, fp32 labels) (distributed_sigmoid_loss.py:28-32)
@@ -188,9 +211,10 @@ class _SigmoidLossFn(torch.autograd.Function):
     def backward(ctx, grad_out):
         dimg, dtxt, dtp, db = ctx.saved_tensors
         idt, tdt, pdt, bdt, pshape, bshape, pdev, bdev = ctx.in_meta
-        g = grad_out.to(torch.float32)
-        gi = (dimg * g).to(idt) if ctx.needs_input_grad[0] else None
-        gt = (dtxt * g).to(tdt) if ctx.needs_input_grad[1] else None
+        g = grad_out.detach().to(torch.float32).reshape(1).contiguous()
+        eng = ctx.engine
+        gi = eng.scale(dimg, g).to(idt) if ctx.needs_input_grad[0] else None
+        gt = eng.scale(dtxt, g).to(tdt) if ctx.needs_input_grad[1] else None
         gp = (dtp * g).reshape(pshape).to(device=pdev, dtype=pdt) if ctx.needs_input_grad[2] else None
         gb = (db * g).reshape(bshape).to(device=bdev, dtype=bdt) if ctx.needs_input_grad[3] else None
         return gi, gt, gp, gb, None

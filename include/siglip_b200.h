@@ -10,7 +10,7 @@
  * except ctx create/destroy and handle import.
  *
  * Data layout: `img`, `txt` are row-major [B, D] bf16 device buffers, 16-byte aligned, D % 8 == 0.
- * `dimg`, `dtxt` are row-major [B, D] fp32. Scalars are fp32 device scalars.
+ * `dimg`, `dtxt` are row-major [B, D] fp32 (or bf16 with SIGLIP_OPT_GRAD_BF16). Scalars are fp32 device scalars.
  */
 #ifndef SIGLIP_B200_H_
 #define SIGLIP_B200_H_
@@ -39,7 +39,8 @@ enum {
   SIGLIP_OPT_KERNEL_TIMING = 3, /* 1: bracket every loss / gradient kernel launch with CUDA events on the caller's stream */
   SIGLIP_OPT_STAGES_LOSS = 4,  /* TMA->MMA pipeline depth of the loss kernel (0 = default) */
   SIGLIP_OPT_STAGES_GRAD = 5,  /* ... of the gradient kernel */
-  SIGLIP_OPT_MCAST = 6         /* cta_group 1 only: 2 (default) = clusters of two CTAs share the B tile by TMA multicast */
+  SIGLIP_OPT_MCAST = 6,        /* cta_group 1 only: 2 (default) = clusters of two CTAs share the B tile by TMA multicast */
+  SIGLIP_OPT_GRAD_BF16 = 7     /* 1: siglip_fwd_bwd writes dimg / dtxt as bf16 [B, D] (the dtype autograd returns for bf16 inputs); default 0 = fp32 */
 };
 
 /* Library / build identification: "siglip_b200 <version> sm_100a". */
@@ -85,7 +86,15 @@ int siglip_ctx_import_handles(siglip_ctx* ctx, const void* all_ranks_bytes, size
  * Collective: every rank of the context's world must call it the same number of times.
  */
 int siglip_fwd_bwd(siglip_ctx* ctx, const void* img, const void* txt, const float* t_prime, const float* bias,
-                   float* loss, float* dimg, float* dtxt, float* dt_prime, float* dbias, void* cuda_stream);
+                   float* loss, void* dimg, void* dtxt, float* dt_prime, float* dbias, void* cuda_stream);
+
+/*
+ * dst = src * (*g) elementwise over `nbytes` of fp32 (is_bf16 = 0) or bf16 (is_bf16 = 1) data: the whole
+ * `backward()` of the module — the fused step already produced the gradients for an upstream gradient of 1
+ * (replaces the autograd graph replay of SURVEY.md §3.2). `g` is a device scalar (grad_output).
+ */
+int siglip_scale(siglip_ctx* ctx, const void* src, void* dst, size_t nbytes, int is_bf16, const float* g,
+                 void* cuda_stream);
 
 /* Forward only (torch.no_grad / evaluation): same collective contract, no gradient work. */
 int siglip_fwd(siglip_ctx* ctx, const void* img, const void* txt, const float* t_prime, const float* bias,

@@ -333,6 +333,36 @@ def test_host_buffer_entry_matches_device_entry():
     eng.close()
 
 
+def test_bf16_gradient_outputs_and_fused_scale():
+    """SIGLIP_OPT_GRAD_BF16: the epilogue writes bf16 gradients = round-to-nearest of the fp32 ones; siglip_scale is
+    the module's whole backward (multi-chunk dimg accumulation stays fp32 until the last chunk)."""
+    B, D = 1024, 256
+    img, txt = _synth(B, D)
+    eng = _engine(B, D, 2)
+    tp, bias = _scal(math.log(10.0)), _scal(-10.0)
+    _, dimg32, dtxt32, _, _ = eng.fwd_bwd(img, txt, tp, bias)
+    _, dimg16, dtxt16, _, _ = eng.fwd_bwd(img, txt, tp, bias, torch.bfloat16)
+    torch.cuda.synchronize()
+    assert dimg16.dtype == torch.bfloat16
+    assert torch.equal(dimg16, dimg32.to(torch.bfloat16)) and torch.equal(dtxt16, dtxt32.to(torch.bfloat16))
+    g = _scal(0.5)
+    assert torch.equal(eng.scale(dimg32, g), dimg32 * 0.5)
+    assert torch.equal(eng.scale(dimg16, g), (dimg16.float() * 0.5).to(torch.bfloat16))
+    eng.close()
+    # two chunks on one GPU (loopback): bf16 dimg of the last chunk == rounded fp32 result
+    W = 2
+    _, txt1 = _synth(B, D, 7)
+    outs = []
+    for dt in (torch.float32, torch.bfloat16):
+        e2 = _engine(B, D, 2, rank_world=(0, W), loopback=True)
+        e2.debug_set_text_chunk(0, txt)
+        e2.debug_set_text_chunk(1, txt1)
+        outs.append(e2.fwd_bwd(img, txt, tp, bias, dt)[1])
+        torch.cuda.synchronize()
+        e2.close()
+    assert torch.equal(outs[1], outs[0].to(torch.bfloat16))
+
+
 def test_kernel_launch_accounting():
     B, D = 512, 128
     img, txt = _synth(B, D)
