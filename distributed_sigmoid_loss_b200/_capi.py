@@ -53,6 +53,7 @@ SIGLIP_OPT_STAGES_LOSS = 4
 SIGLIP_OPT_STAGES_GRAD = 5
 SIGLIP_OPT_MCAST = 6
 SIGLIP_OPT_GRAD_BF16 = 7
+SIGLIP_OPT_OVERLAP_REDUCE = 8
 
 _lib: Optional[ctypes.CDLL] = None
 

@@ -152,6 +152,9 @@ struct siglip_ctx {
   int mcast = 2;                         // B-tile multicast cluster size for cta_group 1 (1 = off)
   int grad_bf16 = 0;                     // dimg / dtxt outputs are bf16 instead of fp32
   float* dimg_acc = nullptr;             // [B, D] fp32 running dimg over the chunks (world > 1)
+  float* dtxt_acc = nullptr;             // [B, D] fp32 running sum of the peers' dtxt contributions (world > 2)
+  const float** final_ptrs_dev = nullptr;  // [4] device: {own slot, last peer's slot} and {dtxt_acc, last peer's slot}
+  int overlap_reduce = 1;                // 1: progressive in-kernel reduction of dtxt, 0: one reduction at the end
   std::vector<cudaEvent_t> ev_loss, ev_grad;  // start, stop, start, stop, ...
   size_t ev_loss_used = 0, ev_grad_used = 0;
   bool loopback = false;
@@ -253,6 +256,7 @@ int run_loss_chunk(siglip_ctx* c, const void* img, const __nv_bfloat16* txt_c, c
 //   prob 1: dtxt_c  = (t/B) * (G^T @ img  [+ g_diag * img])          A = G M-major,  B = img N-major
 int run_grad_chunk(siglip_ctx* c, const void* img, const __nv_bfloat16* txt_c, const float* t_prime, bool own,
                    const float* dimg_add, void* dimg_out, bool dimg_bf16, void* dtxt_out, bool dtxt_bf16,
+                   const float* acc_in, const float* acc_remote, const unsigned int* acc_flag, unsigned int acc_value,
                    cudaStream_t st) {
   const int cg = c->cta_group;
   const int tile_m = 128 * cg;
@@ -289,6 +293,14 @@ int run_grad_chunk(siglip_ctx* c, const void* img, const __nv_bfloat16* txt_c, c
   p.prob[1].out = dtxt_out;
   p.prob[1].out_bf16 = dtxt_bf16 ? 1 : 0;
   p.prob[1].fix_mat = own ? reinterpret_cast<const __nv_bfloat16*>(img) : nullptr;
+  if (acc_remote != nullptr) {
+    p.acc_in = reinterpret_cast<const float4*>(acc_in);
+    p.acc_remote = reinterpret_cast<const float4*>(acc_remote);
+    p.acc_out = reinterpret_cast<float4*>(c->dtxt_acc);
+    p.acc_n4 = static_cast<unsigned long long>(c->B) * c->D / 4;
+    p.acc_wait_flag = acc_flag;
+    p.acc_wait_value = acc_value;
+  }
   p.t_prime = t_prime;
   p.inv_b = 1.0f / static_cast<float>(c->B);
   p.dbg = c->dbg_dev;
@@ -376,9 +388,27 @@ int step_impl(siglip_ctx* c, const void* img, const void* txt, const float* t_pr
       const float* dimg_add = (k > 0) ? c->dimg_acc : nullptr;
       void* dimg_out = last ? dimg : static_cast<void*>(c->dimg_acc);
       void* dtxt_out = (W == 1) ? dtxt : static_cast<void*>(c->slots + cidx * chunk_elems);
+      // progressive dtxt reduction (W > 2): at step k >= 2 fold in the contribution that rank (r - (k-1)) produced
+      // for me at ITS step k-1 (flag value (s-1)*W + k once its gradient kernel of that step has retired)
+      const float* acc_in = nullptr;
+      const float* acc_remote = nullptr;
+      const unsigned int* acc_flag = nullptr;
+      unsigned int acc_value = 0;
+      if (W > 2 && c->overlap_reduce && k >= 2) {
+        const int pr = ((r - (k - 1)) % W + W) % W;
+        acc_in = (k == 2) ? c->slots + r * chunk_elems : c->dtxt_acc;
+        acc_remote = c->peer_slots[pr] + r * chunk_elems;
+        acc_flag = c->flags + 1 * kMaxWorld + pr;
+        acc_value = (s - 1) * static_cast<unsigned int>(W) + static_cast<unsigned int>(k);
+      }
       if ((rc = run_grad_chunk(c, img, txt_c, t_prime, k == 0, dimg_add, dimg_out, last && c->grad_bf16, dtxt_out,
-                               W == 1 && c->grad_bf16, st)))
+                               W == 1 && c->grad_bf16, acc_in, acc_remote, acc_flag, acc_value, st)))
         return rc;
+      if (W > 1 && c->overlap_reduce) {
+        // my contribution for owner cidx is complete: publish step k
+        if ((rc = signal_peers(c, 1, (s - 1) * static_cast<unsigned int>(W) + static_cast<unsigned int>(k + 1), st)))
+          return rc;
+      }
     }
   }
   CKI(siglip::launch_finalize(c->partials, c->num_sms, t_prime, 1.0f / static_cast<float>(c->B), loss,
@@ -389,9 +419,18 @@ int step_impl(siglip_ctx* c, const void* img, const void* txt, const float* t_pr
     if (with_grad) {
       // dtxt of my text rows = sum over ranks of their contribution slot for me: what all_gather's backward
       // (reduce-scatter SUM, torch functional.py:343-354) or the reverse ring (distributed_utils.py:75-77) delivers.
-      if ((rc = signal_peers(c, 1, s, st))) return rc;
-      if ((rc = wait_peers(c, 1, s, st))) return rc;
-      CKI(siglip::launch_reduce_slots(dtxt, c->grad_bf16, c->reduce_ptrs_dev, W, chunk_elems, c->num_sms, st));
+      if (c->overlap_reduce) {
+        // only the contribution produced last (by rank r+1 in its final step) is still outstanding
+        CKI(siglip::launch_wait_flags(c->flags + 1 * kMaxWorld + (r + 1) % W, 1, s * static_cast<unsigned int>(W),
+                                      c->dbg_dev, st));
+        c->launches++;
+        CKI(siglip::launch_reduce_slots(dtxt, c->grad_bf16, c->final_ptrs_dev + (W > 2 ? 2 : 0), 2, chunk_elems,
+                                        c->num_sms, st));
+      } else {
+        if ((rc = signal_peers(c, 1, s * static_cast<unsigned int>(W), st))) return rc;
+        if ((rc = wait_peers(c, 1, s * static_cast<unsigned int>(W), st))) return rc;
+        CKI(siglip::launch_reduce_slots(dtxt, c->grad_bf16, c->reduce_ptrs_dev, W, chunk_elems, c->num_sms, st));
+      }
       c->launches++;
     }
     if ((rc = signal_peers(c, 2, s, st))) return rc;
@@ -467,6 +506,8 @@ int siglip_ctx_create(siglip_ctx** out, int device, int rank, int world, int B, 
     CK(alloc(reinterpret_cast<void**>(&c->txt_all), chunk_elems * world * sizeof(__nv_bfloat16)));
     CK(alloc(reinterpret_cast<void**>(&c->slots), chunk_elems * world * sizeof(float)));
     CK(alloc(reinterpret_cast<void**>(&c->dimg_acc), chunk_elems * sizeof(float)));
+    CK(alloc(reinterpret_cast<void**>(&c->dtxt_acc), chunk_elems * sizeof(float)));
+    CK(alloc(reinterpret_cast<void**>(&c->final_ptrs_dev), 4 * sizeof(float*)));
     CK(alloc(reinterpret_cast<void**>(&c->reduce_ptrs_dev), world * sizeof(float*)));
     CK(alloc(reinterpret_cast<void**>(&c->signal_ptrs_dev), kFlagKinds * world * sizeof(unsigned int*)));
   }
@@ -491,6 +532,9 @@ int siglip_ctx_set_option(siglip_ctx* c, int option, int value) {
       return 0;
     case SIGLIP_OPT_OVERLAP_PULL:
       c->overlap_pull = value ? 1 : 0;
+      return 0;
+    case SIGLIP_OPT_OVERLAP_REDUCE:
+      c->overlap_reduce = value ? 1 : 0;
       return 0;
     case SIGLIP_OPT_GRAD_BF16:
       c->grad_bf16 = value ? 1 : 0;
@@ -564,6 +608,12 @@ int siglip_ctx_import_handles(siglip_ctx* c, const void* all_ranks_bytes, size_t
   std::vector<unsigned int*> sig(kFlagKinds * c->world);
   for (int k = 0; k < kFlagKinds; ++k)
     for (int p = 0; p < c->world; ++p) sig[k * c->world + p] = c->peer_flags[p] + k * kMaxWorld + c->rank;
+  {
+    const int plast = (c->rank + 1) % c->world;   // the peer whose contribution for me is produced last
+    const float* fin[4] = {c->slots + c->rank * chunk_elems, c->peer_slots[plast] + c->rank * chunk_elems,
+                           c->dtxt_acc, c->peer_slots[plast] + c->rank * chunk_elems};
+    CK(cudaMemcpy(c->final_ptrs_dev, fin, sizeof(fin), cudaMemcpyHostToDevice));
+  }
   CK(cudaMemcpy(c->signal_ptrs_dev, sig.data(), sig.size() * sizeof(unsigned int*), cudaMemcpyHostToDevice));
   c->peers_ready = true;
   return 0;
@@ -657,6 +707,12 @@ int siglip_debug_loopback(siglip_ctx* c) {
   std::vector<unsigned int*> sig(kFlagKinds * c->world);
   for (int k = 0; k < kFlagKinds; ++k)
     for (int p = 0; p < c->world; ++p) sig[k * c->world + p] = c->flags + k * kMaxWorld + p;
+  {
+    const int plast = (c->rank + 1) % c->world;   // the peer whose contribution for me is produced last
+    const float* fin[4] = {c->slots + c->rank * chunk_elems, c->peer_slots[plast] + c->rank * chunk_elems,
+                           c->dtxt_acc, c->peer_slots[plast] + c->rank * chunk_elems};
+    CK(cudaMemcpy(c->final_ptrs_dev, fin, sizeof(fin), cudaMemcpyHostToDevice));
+  }
   CK(cudaMemcpy(c->signal_ptrs_dev, sig.data(), sig.size() * sizeof(unsigned int*), cudaMemcpyHostToDevice));
   c->peers_ready = true;
   c->loopback = true;
@@ -828,6 +884,8 @@ void siglip_ctx_destroy(siglip_ctx* c) {
   cudaFree(c->txt16);
   cudaFree(c->slots);
   cudaFree(c->dimg_acc);
+  cudaFree(c->dtxt_acc);
+  cudaFree(c->final_ptrs_dev);
   cudaFree(c->partials);
   cudaFree(c->flags);
   cudaFree(c->scalars);

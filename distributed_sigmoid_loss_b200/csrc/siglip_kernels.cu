@@ -90,6 +90,33 @@ __device__ __forceinline__ double warp_sum(double v) {
   return v;
 }
 
+// Bounded acquire-spin on a flag written by a peer GPU (st.release.sys): >= value, or trap after 20 s.
+__device__ __forceinline__ void wait_peer_flag(const volatile unsigned int* flag, unsigned int value, DebugRecord* dbg,
+                                               unsigned int site) {
+  uint64_t t0 = 0;
+  uint32_t spins = 0;
+  while (true) {
+    unsigned int v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
+    if (v >= value) break;
+    if ((++spins & 0xffu) == 0) {
+      const uint64_t now = globaltimer_ns();
+      if (t0 == 0) t0 = now;
+      if (now - t0 > 20000000000ull) {
+        if (dbg != nullptr && (threadIdx.x & 31) == 0) {
+          dbg->block = blockIdx.x;
+          dbg->thread = threadIdx.x;
+          dbg->aux0 = v;
+          dbg->aux1 = value;
+          dbg->code = site;
+          __threadfence_system();
+        }
+        __trap();
+      }
+    }
+  }
+}
+
 struct TileCoord {
   int prob;
   int m_blk;
@@ -627,30 +654,7 @@ siglip_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_consta
     // chunk's tiles compute (replaces distributed_utils.py:10-27 neighbour_exchange / the all_gather at
     // distributed_sigmoid_loss.py:35). MMA operands are then fed from local memory only.
     if (p.pull_bytes != 0) {
-      if (p.pull_wait_flag != nullptr) {
-        uint64_t t0 = 0;
-        uint32_t spins = 0;
-        while (true) {
-          unsigned int v;
-          asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p.pull_wait_flag) : "memory");
-          if (v >= p.pull_wait_value) break;
-          if ((++spins & 0xffu) == 0) {
-            const uint64_t now = globaltimer_ns();
-            if (t0 == 0) t0 = now;
-            if (now - t0 > 20000000000ull) {
-              if (p.dbg != nullptr && lane == 0) {
-                p.dbg->block = blockIdx.x;
-                p.dbg->thread = threadIdx.x;
-                p.dbg->aux0 = v;
-                p.dbg->aux1 = p.pull_wait_value;
-                p.dbg->code = 5;
-                __threadfence_system();
-              }
-              __trap();
-            }
-          }
-        }
-      }
+      if (p.pull_wait_flag != nullptr) wait_peer_flag(p.pull_wait_flag, p.pull_wait_value, p.dbg, 5);
       const unsigned long long n16 = p.pull_bytes >> 4;
       const unsigned long long nthreads = static_cast<unsigned long long>(gridDim.x) * 64ull;
       unsigned long long i = static_cast<unsigned long long>(blockIdx.x) * 64ull + (threadIdx.x - kAllocWarp * 32);
@@ -689,6 +693,28 @@ siglip_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_consta
           o[q] = pack_16x2<true>(lo, hi);
         }
         dst[i] = make_uint4(o[0], o[1], o[2], o[3]);
+      }
+    }
+    // Progressive cross-rank reduction of the text gradient: while this chunk's tiles compute, add the contribution
+    // a peer finished one step ago (read over NVSwitch P2P) into the local fp32 accumulator. This is the reduce-scatter
+    // of all_gather's backward (torch functional.py:343-354), spread over the steps instead of exposed at the end.
+    if (p.acc_n4 != 0) {
+      if (p.acc_wait_flag != nullptr) wait_peer_flag(p.acc_wait_flag, p.acc_wait_value, p.dbg, 7);
+      const unsigned long long nthreads = static_cast<unsigned long long>(gridDim.x) * 64ull;
+      unsigned long long i = static_cast<unsigned long long>(blockIdx.x) * 64ull + (threadIdx.x - kAllocWarp * 32);
+      for (; i + 3ull * nthreads < p.acc_n4; i += 4ull * nthreads) {
+        float4 r0 = p.acc_remote[i], r1 = p.acc_remote[i + nthreads];
+        float4 r2 = p.acc_remote[i + 2ull * nthreads], r3 = p.acc_remote[i + 3ull * nthreads];
+        const float4 a0 = p.acc_in[i], a1 = p.acc_in[i + nthreads];
+        const float4 a2 = p.acc_in[i + 2ull * nthreads], a3 = p.acc_in[i + 3ull * nthreads];
+        p.acc_out[i] = make_float4(a0.x + r0.x, a0.y + r0.y, a0.z + r0.z, a0.w + r0.w);
+        p.acc_out[i + nthreads] = make_float4(a1.x + r1.x, a1.y + r1.y, a1.z + r1.z, a1.w + r1.w);
+        p.acc_out[i + 2ull * nthreads] = make_float4(a2.x + r2.x, a2.y + r2.y, a2.z + r2.z, a2.w + r2.w);
+        p.acc_out[i + 3ull * nthreads] = make_float4(a3.x + r3.x, a3.y + r3.y, a3.z + r3.z, a3.w + r3.w);
+      }
+      for (; i < p.acc_n4; i += nthreads) {
+        const float4 rr = p.acc_remote[i], aa = p.acc_in[i];
+        p.acc_out[i] = make_float4(aa.x + rr.x, aa.y + rr.y, aa.z + rr.z, aa.w + rr.w);
       }
     }
   }

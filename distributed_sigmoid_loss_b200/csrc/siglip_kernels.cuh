@@ -63,6 +63,13 @@ struct KernelParams {
   uint4* cvt_dst[2];
   unsigned long long cvt_n16[2];
   float cvt_scale;
+  // optional fp32 accumulate job of the same warps: acc_out = acc_in + acc_remote (acc_remote may be peer memory)
+  const float4* acc_in;
+  const float4* acc_remote;
+  float4* acc_out;
+  unsigned long long acc_n4;
+  const volatile unsigned int* acc_wait_flag;
+  unsigned int acc_wait_value;
 };
 
 enum KernelMode { kModeLoss = 0, kModeOut = 1 };

@@ -40,6 +40,7 @@ enum {
   SIGLIP_OPT_STAGES_LOSS = 4,  /* TMA->MMA pipeline depth of the loss kernel (0 = default) */
   SIGLIP_OPT_STAGES_GRAD = 5,  /* ... of the gradient kernel */
   SIGLIP_OPT_MCAST = 6,        /* cta_group 1 only: 2 (default) = clusters of two CTAs share the B tile by TMA multicast */
+  SIGLIP_OPT_OVERLAP_REDUCE = 8, /* 1 (default): fold the peers' dtxt contributions in step by step inside the gradient kernels; 0: one reduction at the end */
   SIGLIP_OPT_GRAD_BF16 = 7     /* 1: siglip_fwd_bwd writes dimg / dtxt as bf16 [B, D] (the dtype autograd returns for bf16 inputs); default 0 = fp32 */
 };
 

@@ -119,25 +119,45 @@ def main() -> int:
         mod = DDPSigmoidLoss(B).to(dev)
         eng = mod.engine_for(B, D, dev)
         tpt, bt = torch.tensor([math.log(10.0)], device=dev), torch.tensor([-10.0], device=dev)
-        for overlap in (1, 0):
-            eng.set_option(_capi.SIGLIP_OPT_OVERLAP_PULL, overlap)
+        from distributed_sigmoid_loss_b200 import SigmoidLossEngine
+
+        def timed(engine, label):
             for _ in range(3):
-                eng.fwd_bwd(img, txt, tpt, bt)
+                engine.fwd_bwd(img, txt, tpt, bt, torch.bfloat16)
             dist.barrier()
             torch.cuda.synchronize()
+            engine.set_option(_capi.SIGLIP_OPT_KERNEL_TIMING, 1)
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
             for _ in range(args.steps):
-                eng.fwd_bwd(img, txt, tpt, bt)
+                engine.fwd_bwd(img, txt, tpt, bt, torch.bfloat16)
             e1.record()
             torch.cuda.synchronize()
+            lm, ln, gm, gn = engine.kernel_times()
+            engine.set_option(_capi.SIGLIP_OPT_KERNEL_TIMING, 0)
             t = torch.tensor([e0.elapsed_time(e1) / args.steps], device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            w = engine.world
             if rank == 0:
                 ms = float(t)
-                print(f"[time W={world}] B={B} D={D} overlap_pull={overlap}: {ms:.3f} ms/step "
-                      f"{world * B / ms * 1e3 / 1e6:.2f} Mpairs/s (global) "
-                      f"{6.0 * B * world * B * D / ms / 1e9:.1f} TFLOP/s per GPU", flush=True)
+                print(f"[time {label} W={w}] B={B} D={D}: {ms:.3f} ms/step ({ms / w:.3f} per chunk) "
+                      f"{w * B / ms * 1e3 / 1e6:.2f} Mpairs/s (global) {6.0 * B * w * B * D / ms / 1e9:.1f} TFLOP/s per GPU; "
+                      f"loss kernel {lm / max(ln, 1):.3f} ms, gradient kernel {gm / max(gn, 1):.3f} ms (rank 0)",
+                      flush=True)
+            return float(t)
+
+        single = SigmoidLossEngine(B, D, dev, rank_world=(0, 1))
+        t1 = timed(single, "single-GPU baseline on every rank")
+        single.close()
+        eng.set_option(_capi.SIGLIP_OPT_OVERLAP_PULL, 1)
+        eng.set_option(_capi.SIGLIP_OPT_OVERLAP_REDUCE, 1)
+        tw = timed(eng, "in-kernel pull + progressive reduce")
+        if rank == 0:
+            print(f"[time] FLOP-normalised weak-scaling efficiency W*t(1)/t(W) = {world * t1 / tw:.3f}", flush=True)
+        eng.set_option(_capi.SIGLIP_OPT_OVERLAP_REDUCE, 0)
+        timed(eng, "in-kernel pull, reduction at the end")
+        eng.set_option(_capi.SIGLIP_OPT_OVERLAP_PULL, 0)
+        timed(eng, "separate copy, reduction at the end")
     flag = torch.tensor([0 if ok else 1], device=dev)
     dist.all_reduce(flag)
     dist.barrier()
