@@ -39,59 +39,64 @@ def _peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
-
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-         "clocks_event_reasons.sw_power_cap")
+    """SM clock / throttle reasons sampled DURING the timed region (B200_PROFILING.md) through NVML from a Python
+    thread every ~5 ms (the C calls release the GIL); falls back to `nvidia-smi -lms` if pynvml is unavailable."""
 
     def __init__(self, gpu_index: int):
         self.gpu_index = gpu_index
-        self.proc = None
-        self.lines = []
+        self.samples = []      # (sm_mhz, reasons_bitmask)
+        self.max_mhz = None
+        self._stop = threading.Event()
         self.thread = None
+        self.nv = None
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--id={self.gpu_index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                 "-lms", "20"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            import pynvml
+
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(self.gpu_index)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
         except Exception:
-            self.proc = None
+            self.nv = None
             return
-        self.thread = threading.Thread(target=self._pump, daemon=True)
+        self.thread = threading.Thread(target=self._run, daemon=True)
         self.thread.start()
 
-    def _pump(self):
-        for line in self.proc.stdout:
-            self.lines.append(line.strip())
-
-    def stop(self):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except Exception:
-            self.proc.kill()
-        clocks, maxes, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
-            f = [x.strip() for x in ln.split(",")]
-            if len(f) < 9:
-                continue
+    def _run(self):
+        nv = self.nv
+        while not self._stop.is_set():
             try:
-                clocks.append(float(f[1]))
-                maxes.append(float(f[2]))
-            except ValueError:
-                continue
-            for name, val in zip(names, f[5:9]):
-                if val.lower().startswith("active"):
-                    reasons.add(name)
-        clocks.sort()
-        med = clocks[len(clocks) // 2] if clocks else None
-        return {"sm_mhz": med, "sm_max_mhz": max(maxes) if maxes else None, "reasons": sorted(reasons),
-                "samples": len(clocks)}
+                mhz = float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                reasons = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+                self.samples.append((mhz, reasons))
+            except Exception:
+                pass
+            time.sleep(0.005)
+
+    def mark(self):
+        """Index of the next sample: call at the start of the timed region."""
+        return len(self.samples)
+
+    def stop(self, first: int = 0):
+        if self.nv is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvml unavailable"], "samples": 0}
+        self._stop.set()
+        self.thread.join(timeout=1)
+        nv = self.nv
+        sel = self.samples[first:] or self.samples
+        clocks = sorted(s[0] for s in sel)
+        mask = 0
+        for _, r in sel:
+            mask |= r
+        names = {"hw_slowdown": nv.nvmlClocksThrottleReasonHwSlowdown,
+                 "hw_thermal_slowdown": nv.nvmlClocksThrottleReasonHwThermalSlowdown,
+                 "sw_thermal_slowdown": nv.nvmlClocksThrottleReasonSwThermalSlowdown,
+                 "sw_power_cap": nv.nvmlClocksThrottleReasonSwPowerCap}
+        reasons = sorted(k for k, bit in names.items() if mask & bit)
+        return {"sm_mhz": clocks[len(clocks) // 2] if clocks else None, "sm_max_mhz": self.max_mhz,
+                "reasons": reasons, "samples": len(sel)}
 
 
 def synth(rank: int, B: int, D: int):
@@ -229,7 +234,7 @@ def run_ours(args):
 
     sampler = ClockSampler(local_rank)
     if rank == 0:
-        sampler.start()          # covers warm-up + timed region (both under load); 20 ms period
+        sampler.start()          # NVML thread, 5 ms period; samples from the timed region are reported
     for _ in range(max(args.warmup, 3)):
         step()
     barrier()
@@ -237,12 +242,13 @@ def run_ours(args):
     launches0 = eng.launch_count
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    first_sample = sampler.mark()
     e0.record()
     for _ in range(args.steps):
         loss = step()
     e1.record()
     barrier()
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = sampler.stop(first_sample) if rank == 0 else None
     ms_total = e0.elapsed_time(e1)
     if world > 1:
         t = torch.tensor([ms_total], device=dev)

@@ -226,7 +226,8 @@ int run_loss_chunk(siglip_ctx* c, const void* img, const __nv_bfloat16* txt_c, c
   p.pull_bytes = pull_bytes;
   p.pull_wait_flag = pull_flag;
   p.pull_wait_value = pull_value;
-  if (store_g) {  // training step: the gradient kernel of this chunk needs fp16 copies of its B operands
+  if (store_g && getenv("SIGLIP_DEBUG_NO_GSTORE")) p.store_g = 0;  // timing experiments only (wrong gradients)
+  if (store_g && !getenv("SIGLIP_DEBUG_NO_CVT")) {  // training step: the gradient kernel needs fp16 B operands
     const unsigned long long n16 = static_cast<unsigned long long>(c->B) * c->D * sizeof(__nv_bfloat16) / 16;
     p.cvt_scale = kXScale;
     p.cvt_src[0] = reinterpret_cast<const uint4*>(txt_c);
