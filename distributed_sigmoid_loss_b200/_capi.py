@@ -26,6 +26,9 @@ EXPORTED_SYMBOLS = (
     "siglip_ctx_handle_bytes",
     "siglip_ctx_export_handles",
     "siglip_ctx_import_handles",
+    "siglip_forward",
+    "siglip_backward",
+    "siglip_ctx_saved_generation",
     "siglip_fwd_bwd",
     "siglip_fwd",
     "siglip_fwd_bwd_host",
@@ -102,6 +105,12 @@ def lib() -> ctypes.CDLL:
     L.siglip_ctx_export_handles.restype = ci
     L.siglip_ctx_import_handles.argtypes = [vp, vp, cs]
     L.siglip_ctx_import_handles.restype = ci
+    L.siglip_forward.argtypes = [vp, vp, vp, vp, vp, vp, ci, vp]
+    L.siglip_forward.restype = ci
+    L.siglip_backward.argtypes = [vp] * 10
+    L.siglip_backward.restype = ci
+    L.siglip_ctx_saved_generation.argtypes = [vp]
+    L.siglip_ctx_saved_generation.restype = ctypes.c_ulonglong
     L.siglip_fwd_bwd.argtypes = [vp] * 11
     L.siglip_fwd_bwd.restype = ci
     L.siglip_fwd.argtypes = [vp] * 7

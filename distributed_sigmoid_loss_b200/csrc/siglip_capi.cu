@@ -106,7 +106,10 @@ constexpr float kGScale = 16384.0f;
 // (L2-normalised embeddings live in [~1e-4, 1]); the conversion runs inside the loss kernel's idle warps.
 constexpr float kXScale = 16.0f;
 constexpr int kMaxWorld = 32;
-constexpr int kFlagKinds = 3;  // 0: text ready, 1: dtxt slots ready, 2: step done
+// flags[kind][rank]: counters written by peers with st.release.sys
+//   0 text of forward #n is in place        1 dtxt contribution of backward #n, gradient slot j is complete
+//   2 forward #n finished pulling everyone's text     3 backward #n finished reading everyone's contributions
+constexpr int kFlagKinds = 4;
 
 struct IpcBlob {
   cudaIpcMemHandle_t txt;
@@ -123,41 +126,43 @@ struct IpcBlob {
 struct siglip_ctx {
   int device = 0, rank = 0, world = 1, B = 0, D = 0, Bp = 0;
   int num_sms = 0;
+  // options
   int cta_group = 2;
-  int overlap_pull = 1;
-  __nv_bfloat16* txt_all = nullptr;  // [world][B, D]; slot `rank` is what the peers pull
-  __nv_bfloat16* G = nullptr;        // [Bp, Bp] sigma operand of the current chunk (fp16 bits, scaled by kGScale)
-  __nv_bfloat16* img16 = nullptr;    // [B, D] fp16 copy (x kXScale) of the images, operand of the dtxt contraction
-  __nv_bfloat16* txt16 = nullptr;    // [B, D] fp16 copy (x kXScale) of the current text chunk, operand of dimg
-  float* g_diag = nullptr;           // [B]
-  float* slots = nullptr;            // [world][B, D] fp32 dtxt contributions, slot c is for owner c (world > 1)
-  double* partials = nullptr;        // [num_sms][4]
-  unsigned int* flags = nullptr;     // [kFlagKinds][kMaxWorld]
-  float* scalars = nullptr;          // [8] device scalars for the host API / debug
+  int overlap_pull = 1;                  // pull the next text chunk inside the loss kernel
+  int overlap_reduce = 1;                // fold the peers' dtxt contributions inside the gradient kernels
+  int kernel_timing = 0;
+  int stages_loss = 0, stages_grad = 0;  // 0 = kernel default
+  int mcast = 2;                         // B-tile multicast cluster size for cta_group 1 (1 = off)
+  int grad_bf16 = 0;                     // dimg / dtxt outputs are bf16 instead of fp32
+  // workspaces
+  __nv_bfloat16* txt_all = nullptr;      // [world][B, D] bf16; slot `rank` is what the peers pull (world > 1)
+  __nv_bfloat16* G[kMaxWorld] = {};      // per step k: [Bp, Bp] sigma operand (fp16 bits x kGScale), diagonal zeroed
+  __nv_bfloat16* img16 = nullptr;        // [B, D] fp16 (x kXScale) images: B operand of the dtxt contraction
+  __nv_bfloat16* txt16 = nullptr;        // [world][B, D] fp16 (x kXScale) text chunk of step k: B operand of dimg
+  float* g_diag = nullptr;               // [Bp] fp32 positive-pair terms -sigma(-z_ii)
+  float* slots = nullptr;                // [world][B, D] fp32 dtxt contributions, slot c is for owner c (world > 1)
+  float* dimg_acc = nullptr;             // [B, D] fp32 running dimg over the chunks (world > 1)
+  float* dtxt_acc = nullptr;             // [B, D] fp32 running sum of the peers' contributions (world > 1)
+  double* partials = nullptr;            // [num_sms][4]
+  unsigned int* flags = nullptr;         // [kFlagKinds][kMaxWorld]
+  float* scalars = nullptr;              // [16] device scalars: host API staging, saved dt'/dbias of the last forward
   // peers (index = rank); own entries point at local memory
   __nv_bfloat16* peer_txt[kMaxWorld] = {};
   float* peer_slots[kMaxWorld] = {};
   unsigned int* peer_flags[kMaxWorld] = {};
   bool peers_ready = false;
-  const float** reduce_ptrs_dev = nullptr;   // [world] device array: peer_slots[p] + rank*B*D
-  unsigned int** signal_ptrs_dev = nullptr;  // [kFlagKinds][world] device array
-  unsigned int step = 0;
+  bool loopback = false;
+  const float** reduce_ptrs_dev = nullptr;   // [world] peer_slots[p] + rank*B*D  (reduction-at-the-end variant)
+  const float** final_ptrs_dev = nullptr;    // [2] {dtxt_acc, own slot}: the local last add of the progressive variant
+  unsigned int** signal_ptrs_dev = nullptr;  // [kFlagKinds][world]
+  unsigned int n_fwd = 0, n_bwd = 0;         // forward / backward passes issued (flag counters)
+  unsigned long long gen = 0;                // generation of the state saved for backward (0 = none)
   DebugRecord* dbg_host = nullptr;
   DebugRecord* dbg_dev = nullptr;
   unsigned long long launches = 0;
   size_t workspace_bytes = 0;
-  // optional per-kernel CUDA-event timing (SIGLIP_OPT_KERNEL_TIMING): pairs recorded on the caller's stream
-  int kernel_timing = 0;
-  int stages_loss = 0, stages_grad = 0;  // 0 = kernel default
-  int mcast = 2;                         // B-tile multicast cluster size for cta_group 1 (1 = off)
-  int grad_bf16 = 0;                     // dimg / dtxt outputs are bf16 instead of fp32
-  float* dimg_acc = nullptr;             // [B, D] fp32 running dimg over the chunks (world > 1)
-  float* dtxt_acc = nullptr;             // [B, D] fp32 running sum of the peers' dtxt contributions (world > 2)
-  const float** final_ptrs_dev = nullptr;  // [4] device: {own slot, last peer's slot} and {dtxt_acc, last peer's slot}
-  int overlap_reduce = 1;                // 1: progressive in-kernel reduction of dtxt, 0: one reduction at the end
   std::vector<cudaEvent_t> ev_loss, ev_grad;  // start, stop, start, stop, ...
   size_t ev_loss_used = 0, ev_grad_used = 0;
-  bool loopback = false;
   // host-API staging
   __nv_bfloat16* h_img = nullptr;
   __nv_bfloat16* h_txt = nullptr;
@@ -166,6 +171,8 @@ struct siglip_ctx {
 };
 
 namespace {
+
+constexpr int kSavedScalars = 8;  // scalars[8], scalars[9]: dt', dbias of the last forward for upstream gradient 1
 
 int check_dbg(siglip_ctx* c, const char* where) {
   if (c->dbg_host != nullptr && c->dbg_host->code != 0) {
@@ -189,18 +196,41 @@ int timing_mark(siglip_ctx* c, std::vector<cudaEvent_t>& evs, size_t& used, cuda
   return 0;
 }
 
-// The loss kernel over one text chunk: S = img @ txt_c^T on tcgen05, fused scale/bias/log-sigmoid/reduce.
-int run_loss_chunk(siglip_ctx* c, const void* img, const __nv_bfloat16* txt_c, const float* t_prime,
-                   const float* bias, bool own, bool store_g, bool accumulate, bool convert_img,
-                   const void* pull_src, void* pull_dst, size_t pull_bytes, const unsigned int* pull_flag,
-                   unsigned int pull_value, cudaStream_t st) {
+// Sigma operands are allocated on first use: one per step of the chunk schedule (world of them when training).
+int ensure_g(siglip_ctx* c, int k) {
+  if (c->G[k] != nullptr) return 0;
+  const size_t bytes = static_cast<size_t>(c->Bp) * c->Bp * sizeof(__nv_bfloat16);
+  CK(cudaMalloc(reinterpret_cast<void**>(&c->G[k]), bytes));
+  c->workspace_bytes += bytes;
+  return 0;
+}
+
+struct PullJob {
+  const void* src = nullptr;
+  void* dst = nullptr;
+  size_t bytes = 0;
+  const unsigned int* flag = nullptr;
+  unsigned int value = 0;
+};
+
+// The loss kernel over the text chunk of step k: S = img @ txt_c^T on tcgen05, fused scale/bias/log-sigmoid/reduce.
+// save: also write the sigma operand G[k] (+ g_diag on the own chunk) and the fp16 copies the gradient kernel needs.
+int run_loss_chunk(siglip_ctx* c, int k, const void* img, const __nv_bfloat16* txt_c, const float* t_prime,
+                   const float* bias, bool save, const PullJob& pull, cudaStream_t st) {
   const int cg = c->cta_group;
   const int tile_m = 128 * cg;
-  CUtensorMap tmA, tmB;
+  const bool own = (k == 0);
   int rc;
+  if ((rc = ensure_g(c, save ? k : 0))) return rc;
+  __nv_bfloat16* G = c->G[save ? k : 0];
+  CUtensorMap tmA, tmB, tmG;
   if ((rc = encode_operand(&tmA, img, c->B, c->D, c->D, 0, 128))) return rc;
   const int mc = (cg == 1) ? c->mcast : 1;
   if ((rc = encode_operand(&tmB, txt_c, c->B, c->D, c->D, 0, 256 / (cg * mc)))) return rc;
+  // store map of the sigma operand: [B, B] inside the padded [Bp, Bp] buffer, one 32x32 slab per TMA store
+  if ((rc = encode_bf16_2d(&tmG, G, (uint64_t)c->B, (uint64_t)c->B, (uint64_t)c->Bp, 32, 32,
+                           CU_TENSOR_MAP_SWIZZLE_64B)))
+    return rc;
   KernelParams p;
   memset(&p, 0, sizeof(p));
   p.nprob = 1;
@@ -212,38 +242,34 @@ int run_loss_chunk(siglip_ctx* c, const void* img, const __nv_bfloat16* txt_c, c
   p.t_prime = t_prime;
   p.bias = bias;
   p.inv_b = 1.0f / static_cast<float>(c->B);
-  p.G = c->G;
+  p.G = G;
   p.ldg = c->Bp;
   p.g_diag = c->g_diag;
   p.own_chunk = own ? 1 : 0;
-  p.store_g = store_g ? 1 : 0;
+  p.store_g = save ? 1 : 0;
   p.g_scale = kGScale;
   p.partials = c->partials;
-  p.accumulate_partials = accumulate ? 1 : 0;
+  p.accumulate_partials = 1;  // the partials are zeroed at the start of every forward
   p.dbg = c->dbg_dev;
-  p.pull_src = reinterpret_cast<const uint4*>(pull_src);
-  p.pull_dst = reinterpret_cast<uint4*>(pull_dst);
-  p.pull_bytes = pull_bytes;
-  p.pull_wait_flag = pull_flag;
-  p.pull_wait_value = pull_value;
-  if (store_g && getenv("SIGLIP_DEBUG_NO_GSTORE")) p.store_g = 0;  // timing experiments only (wrong gradients)
-  if (store_g && !getenv("SIGLIP_DEBUG_NO_CVT")) {  // training step: the gradient kernel needs fp16 B operands
-    const unsigned long long n16 = static_cast<unsigned long long>(c->B) * c->D * sizeof(__nv_bfloat16) / 16;
+  p.pull_src = reinterpret_cast<const uint4*>(pull.src);
+  p.pull_dst = reinterpret_cast<uint4*>(pull.dst);
+  p.pull_bytes = pull.bytes;
+  p.pull_wait_flag = pull.flag;
+  p.pull_wait_value = pull.value;
+  if (save && getenv("SIGLIP_DEBUG_NO_GSTORE")) p.store_g = 0;  // timing experiments only (wrong gradients)
+  if (save && !getenv("SIGLIP_DEBUG_NO_CVT")) {
+    const size_t chunk_elems = static_cast<size_t>(c->B) * c->D;
+    const unsigned long long n16 = chunk_elems * sizeof(__nv_bfloat16) / 16;
     p.cvt_scale = kXScale;
     p.cvt_src[0] = reinterpret_cast<const uint4*>(txt_c);
-    p.cvt_dst[0] = reinterpret_cast<uint4*>(c->txt16);
+    p.cvt_dst[0] = reinterpret_cast<uint4*>(c->txt16 + static_cast<size_t>(k) * chunk_elems);
     p.cvt_n16[0] = n16;
-    if (convert_img) {
+    if (own) {
       p.cvt_src[1] = reinterpret_cast<const uint4*>(img);
       p.cvt_dst[1] = reinterpret_cast<uint4*>(c->img16);
       p.cvt_n16[1] = n16;
     }
   }
-  // store map of the sigma operand: [B, B] bf16 inside the padded [Bp, Bp] buffer, one 32x32 slab per TMA store
-  CUtensorMap tmG;
-  if ((rc = encode_bf16_2d(&tmG, c->G, (uint64_t)c->B, (uint64_t)c->B, (uint64_t)c->Bp, 32, 32,
-                           CU_TENSOR_MAP_SWIZZLE_64B)))
-    return rc;
   if ((rc = timing_mark(c, c->ev_loss, c->ev_loss_used, st))) return rc;
   CKI(siglip::launch_gemm(cg, siglip::kModeLoss, c->stages_loss, mc, &tmA, &tmB, &tmA, &tmB, &tmG, p, c->num_sms,
                           st));
@@ -252,20 +278,28 @@ int run_loss_chunk(siglip_ctx* c, const void* img, const __nv_bfloat16* txt_c, c
   return 0;
 }
 
-// The two gradient contractions of one chunk in one launch:
-//   prob 0: dimg (+)= (t/B) * (G @ txt_c  [+ g_diag * txt_own])      A = G K-major,  B = txt_c N-major
-//   prob 1: dtxt_c  = (t/B) * (G^T @ img  [+ g_diag * img])          A = G M-major,  B = img N-major
-int run_grad_chunk(siglip_ctx* c, const void* img, const __nv_bfloat16* txt_c, const float* t_prime, bool own,
-                   const float* dimg_add, void* dimg_out, bool dimg_bf16, void* dtxt_out, bool dtxt_bf16,
-                   const float* acc_in, const float* acc_remote, const unsigned int* acc_flag, unsigned int acc_value,
-                   cudaStream_t st) {
+struct FoldJob {   // dtxt_acc = (in ? in : 0) + remote   by the idle warps of a gradient kernel
+  const float* in = nullptr;
+  const float* remote = nullptr;
+  const unsigned int* flag = nullptr;
+  unsigned int value = 0;
+};
+
+// The two gradient contractions of the chunk of step k in one launch (g = upstream gradient, device scalar or null):
+//   prob 0: dimg (+)= g (t/B) (G @ txt_c  [+ g_diag * txt_own])      A = G K-major,  B = txt16[k] N-major
+//   prob 1: dtxt_c  = g (t/B) (G^T @ img  [+ g_diag * img])          A = G M-major,  B = img16 N-major
+int run_grad_chunk(siglip_ctx* c, int k, const void* img, const __nv_bfloat16* txt_c, const float* t_prime,
+                   const float* grad_out, const float* dimg_add, void* dimg_out, bool dimg_bf16, void* dtxt_out,
+                   bool dtxt_bf16, const FoldJob& fold, cudaStream_t st) {
   const int cg = c->cta_group;
   const int tile_m = 128 * cg;
+  const bool own = (k == 0);
+  const size_t chunk_elems = static_cast<size_t>(c->B) * c->D;
   CUtensorMap tmA0, tmB0, tmA1, tmB1;
   int rc;
-  if ((rc = encode_operand(&tmA0, c->G, c->B, c->B, c->Bp, 0, 128))) return rc;
-  if ((rc = encode_operand(&tmB0, c->txt16, c->D, c->B, c->D, 1, 0))) return rc;
-  if ((rc = encode_operand(&tmA1, c->G, c->B, c->B, c->Bp, 1, 0))) return rc;
+  if ((rc = encode_operand(&tmA0, c->G[k], c->B, c->B, c->Bp, 0, 128))) return rc;
+  if ((rc = encode_operand(&tmB0, c->txt16 + static_cast<size_t>(k) * chunk_elems, c->D, c->B, c->D, 1, 0))) return rc;
+  if ((rc = encode_operand(&tmA1, c->G[k], c->B, c->B, c->Bp, 1, 0))) return rc;
   if ((rc = encode_operand(&tmB1, c->img16, c->D, c->B, c->D, 1, 0))) return rc;
   KernelParams p;
   memset(&p, 0, sizeof(p));
@@ -294,15 +328,16 @@ int run_grad_chunk(siglip_ctx* c, const void* img, const __nv_bfloat16* txt_c, c
   p.prob[1].out = dtxt_out;
   p.prob[1].out_bf16 = dtxt_bf16 ? 1 : 0;
   p.prob[1].fix_mat = own ? reinterpret_cast<const __nv_bfloat16*>(img) : nullptr;
-  if (acc_remote != nullptr) {
-    p.acc_in = reinterpret_cast<const float4*>(acc_in);
-    p.acc_remote = reinterpret_cast<const float4*>(acc_remote);
+  if (fold.remote != nullptr) {
+    p.acc_in = reinterpret_cast<const float4*>(fold.in);
+    p.acc_remote = reinterpret_cast<const float4*>(fold.remote);
     p.acc_out = reinterpret_cast<float4*>(c->dtxt_acc);
-    p.acc_n4 = static_cast<unsigned long long>(c->B) * c->D / 4;
-    p.acc_wait_flag = acc_flag;
-    p.acc_wait_value = acc_value;
+    p.acc_n4 = static_cast<unsigned long long>(chunk_elems / 4);
+    p.acc_wait_flag = fold.flag;
+    p.acc_wait_value = fold.value;
   }
   p.t_prime = t_prime;
+  p.grad_out = grad_out;
   p.inv_b = 1.0f / static_cast<float>(c->B);
   p.dbg = c->dbg_dev;
   if ((rc = timing_mark(c, c->ev_grad, c->ev_grad_used, st))) return rc;
@@ -325,116 +360,142 @@ int wait_peers(siglip_ctx* c, int kind, unsigned int value, cudaStream_t st) {
   return 0;
 }
 
-int step_impl(siglip_ctx* c, const void* img, const void* txt, const float* t_prime, const float* bias, float* loss,
-              void* dimg, void* dtxt, float* dt_prime, float* dbias, bool with_grad, cudaStream_t st) {
+int wait_one(siglip_ctx* c, int kind, int rank, unsigned int value, cudaStream_t st) {
+  CKI(siglip::launch_wait_flags(c->flags + kind * kMaxWorld + rank, 1, value, c->dbg_dev, st));
+  c->launches++;
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Forward: W loss kernels. Step k scores my images against the text chunk owned by rank (r + k) % W — the pairs the
+// reference's ring covers (rwightman_sigmoid_loss.py:108-122) without the hop-by-hop forwarding: every chunk is pulled
+// straight from its owner through the NVSwitch by the idle warps of the loss kernel of the previous step.
+// ---------------------------------------------------------------------------------------------------------------
+int forward_impl(siglip_ctx* c, const void* img, const void* txt, const float* t_prime, const float* bias, float* loss,
+                 bool save, cudaStream_t st) {
   if (c == nullptr || img == nullptr || txt == nullptr || t_prime == nullptr || bias == nullptr || loss == nullptr)
     return fail(SIGLIP_ERR_INVALID, "null argument");
-  if (with_grad && (dimg == nullptr || dtxt == nullptr || dt_prime == nullptr || dbias == nullptr))
-    return fail(SIGLIP_ERR_INVALID, "null gradient pointer");
   if (c->world > 1 && !c->peers_ready)
     return fail(SIGLIP_ERR_STATE, "world > 1 but peer handles were not imported (siglip_ctx_import_handles)");
   int rc;
-  if ((rc = check_dbg(c, "siglip step (previous launch)"))) return rc;
+  if ((rc = check_dbg(c, "siglip forward (previous launch)"))) return rc;
   CK(cudaSetDevice(c->device));
   const int W = c->world, r = c->rank;
   const size_t chunk_elems = static_cast<size_t>(c->B) * c->D;
   const size_t chunk_bytes = chunk_elems * sizeof(__nv_bfloat16);
-  c->step++;
-  const unsigned int s = c->step;
+  const unsigned int s = ++c->n_fwd;
+  if (save) c->gen = 0;  // the saved state is being overwritten; valid again once everything is enqueued
 
   const __nv_bfloat16* own_txt = reinterpret_cast<const __nv_bfloat16*>(txt);
   if (W > 1) {
-    // peers must have finished reading my text slot / dtxt slots of the previous step before I overwrite them
+    // peers must have finished pulling my text slot in their previous forward before I overwrite it
     if ((rc = wait_peers(c, 2, s - 1, st))) return rc;
     CK(cudaMemcpyAsync(c->txt_all + r * chunk_elems, txt, chunk_bytes, cudaMemcpyDeviceToDevice, st));
     if ((rc = signal_peers(c, 0, s, st))) return rc;
     own_txt = c->txt_all + r * chunk_elems;
   }
-
   CKI(siglip::launch_zero_partials(c->partials, c->num_sms, st));
   c->launches++;
-
-  // Chunk schedule: step k scores my images against the text chunk owned by rank (r + k) % W — the order in
-  // which the reference's ring delivers them (rwightman_sigmoid_loss.py:108-122), without the hop-by-hop
-  // forwarding: every chunk is pulled straight from its owner through the NVSwitch.
   for (int k = 0; k < W; ++k) {
     const int cidx = (r + k) % W;
     const __nv_bfloat16* txt_c = (k == 0) ? own_txt : c->txt_all + cidx * chunk_elems;
-    const void* pull_src = nullptr;
-    void* pull_dst = nullptr;
-    size_t pull_bytes = 0;
-    const unsigned int* pull_flag = nullptr;
+    PullJob pull;
     if (k + 1 < W) {
       const int nxt = (r + k + 1) % W;
-      pull_src = c->peer_txt[nxt] + nxt * chunk_elems;
-      pull_dst = c->txt_all + nxt * chunk_elems;
-      pull_bytes = chunk_bytes;
-      pull_flag = c->flags + 0 * kMaxWorld + nxt;
+      pull.src = c->peer_txt[nxt] + nxt * chunk_elems;
+      pull.dst = c->txt_all + nxt * chunk_elems;
+      pull.bytes = chunk_bytes;
+      pull.flag = c->flags + 0 * kMaxWorld + nxt;
+      pull.value = s;
+      if (!c->overlap_pull) {
+        // un-overlapped variant (A/B measurements): wait + copy as separate stream operations
+        if ((rc = wait_one(c, 0, nxt, s, st))) return rc;
+        CK(cudaMemcpyAsync(pull.dst, pull.src, pull.bytes, cudaMemcpyDefault, st));
+        pull = PullJob();
+      }
     }
-    if (!c->overlap_pull && pull_bytes != 0) {
-      // un-overlapped variant (for A/B measurements): wait + copy as separate stream operations
-      if ((rc = wait_peers(c, 0, s, st))) return rc;
-      CK(cudaMemcpyAsync(pull_dst, pull_src, pull_bytes, cudaMemcpyDefault, st));
-      pull_bytes = 0;
-      pull_src = pull_dst = nullptr;
-      pull_flag = nullptr;
+    if ((rc = run_loss_chunk(c, k, img, txt_c, t_prime, bias, save, pull, st))) return rc;
+  }
+  // loss, and (for backward) dt' / dbias for an upstream gradient of 1
+  CKI(siglip::launch_finalize(c->partials, c->num_sms, t_prime, 1.0f / static_cast<float>(c->B), loss,
+                              c->scalars + kSavedScalars, c->scalars + kSavedScalars + 1, st));
+  c->launches++;
+  if (W > 1) {
+    if ((rc = signal_peers(c, 2, s, st))) return rc;
+  }
+  CK(cudaGetLastError());
+  if (save) {
+    static unsigned long long next_gen = 0;
+    c->gen = ++next_gen;
+  }
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Backward: W gradient kernels over the sigma operands the forward saved, the OWN chunk last. Gradient slot j = 1..W
+// handles step k = j (j < W) or k = 0 (j == W). My contribution to owner (r + k) % W goes to a local fp32 slot and is
+// published with flag value (n-1) W + j; one slot later the owner folds it into its accumulator from inside its own
+// gradient kernel (P2P loads over NVSwitch), so every remote contribution has a whole gradient kernel of slack and
+// only a local add remains at the end: this is all_gather's backward (reduce-scatter SUM, torch functional.py:343-354;
+// reverse ring, distributed_utils.py:75-77, 94-98) without an exposed collective.
+// ---------------------------------------------------------------------------------------------------------------
+int backward_impl(siglip_ctx* c, const void* img, const void* txt, const float* t_prime, const float* grad_out,
+                  void* dimg, void* dtxt, float* dt_prime, float* dbias, cudaStream_t st) {
+  if (c == nullptr || img == nullptr || txt == nullptr || t_prime == nullptr || dimg == nullptr || dtxt == nullptr)
+    return fail(SIGLIP_ERR_INVALID, "null argument");
+  if (c->gen == 0) return fail(SIGLIP_ERR_STATE, "no forward state saved for backward (call siglip_forward with save = 1)");
+  int rc;
+  if ((rc = check_dbg(c, "siglip backward (previous launch)"))) return rc;
+  CK(cudaSetDevice(c->device));
+  const int W = c->world, r = c->rank;
+  const size_t chunk_elems = static_cast<size_t>(c->B) * c->D;
+  const unsigned int n = ++c->n_bwd;
+  const unsigned int base = (n - 1) * static_cast<unsigned int>(W);
+  if (W > 1) {
+    // peers must have finished reading my contribution slots of the previous backward before I overwrite them
+    if ((rc = wait_peers(c, 3, n - 1, st))) return rc;
+  }
+  // bf16 text of the own chunk (positive-pair term of dimg): my gathered slot, or the caller's tensor for one rank
+  const __nv_bfloat16* own_txt =
+      (W > 1) ? c->txt_all + r * chunk_elems : reinterpret_cast<const __nv_bfloat16*>(txt);
+  for (int j = 1; j <= W; ++j) {
+    const int k = (j < W) ? j : 0;
+    const int cidx = (r + k) % W;
+    const bool last = (j == W);
+    const __nv_bfloat16* txt_c = (k == 0) ? own_txt : nullptr;
+    const float* dimg_add = (j > 1) ? c->dimg_acc : nullptr;
+    void* dimg_out = last ? dimg : static_cast<void*>(c->dimg_acc);
+    void* dtxt_out = (W == 1) ? dtxt : static_cast<void*>(c->slots + cidx * chunk_elems);
+    FoldJob fold;
+    if (W > 1 && c->overlap_reduce && j >= 2) {
+      // the contribution rank p = r - (j-1) produced for me in ITS gradient slot j-1
+      const int pr = ((r - (j - 1)) % W + W) % W;
+      fold.in = (j == 2) ? nullptr : c->dtxt_acc;
+      fold.remote = c->peer_slots[pr] + r * chunk_elems;
+      fold.flag = c->flags + 1 * kMaxWorld + pr;
+      fold.value = base + static_cast<unsigned int>(j - 1);
     }
-    if ((rc = run_loss_chunk(c, img, txt_c, t_prime, bias, k == 0, with_grad, true, k == 0, pull_src, pull_dst, pull_bytes,
-                             pull_flag, s, st)))
+    if ((rc = run_grad_chunk(c, k, img, txt_c, t_prime, grad_out, dimg_add, dimg_out, last && c->grad_bf16, dtxt_out,
+                             W == 1 && c->grad_bf16, fold, st)))
       return rc;
-    if (with_grad) {
-      // dimg accumulates over the chunks in an fp32 workspace; the last chunk writes the caller's buffer (fp32 or
-      // bf16). dtxt goes to the caller directly when there is one rank, else to this rank's slot for the owner.
-      const bool last = (k == W - 1);
-      const float* dimg_add = (k > 0) ? c->dimg_acc : nullptr;
-      void* dimg_out = last ? dimg : static_cast<void*>(c->dimg_acc);
-      void* dtxt_out = (W == 1) ? dtxt : static_cast<void*>(c->slots + cidx * chunk_elems);
-      // progressive dtxt reduction (W > 2): at step k >= 2 fold in the contribution that rank (r - (k-1)) produced
-      // for me at ITS step k-1 (flag value (s-1)*W + k once its gradient kernel of that step has retired)
-      const float* acc_in = nullptr;
-      const float* acc_remote = nullptr;
-      const unsigned int* acc_flag = nullptr;
-      unsigned int acc_value = 0;
-      if (W > 2 && c->overlap_reduce && k >= 2) {
-        const int pr = ((r - (k - 1)) % W + W) % W;
-        acc_in = (k == 2) ? c->slots + r * chunk_elems : c->dtxt_acc;
-        acc_remote = c->peer_slots[pr] + r * chunk_elems;
-        acc_flag = c->flags + 1 * kMaxWorld + pr;
-        acc_value = (s - 1) * static_cast<unsigned int>(W) + static_cast<unsigned int>(k);
-      }
-      if ((rc = run_grad_chunk(c, img, txt_c, t_prime, k == 0, dimg_add, dimg_out, last && c->grad_bf16, dtxt_out,
-                               W == 1 && c->grad_bf16, acc_in, acc_remote, acc_flag, acc_value, st)))
-        return rc;
-      if (W > 1 && c->overlap_reduce) {
-        // my contribution for owner cidx is complete: publish step k
-        if ((rc = signal_peers(c, 1, (s - 1) * static_cast<unsigned int>(W) + static_cast<unsigned int>(k + 1), st)))
-          return rc;
-      }
+    if (W > 1 && (!last || !c->overlap_reduce)) {
+      if ((rc = signal_peers(c, 1, base + static_cast<unsigned int>(j), st))) return rc;
     }
   }
-  CKI(siglip::launch_finalize(c->partials, c->num_sms, t_prime, 1.0f / static_cast<float>(c->B), loss,
-                              with_grad ? dt_prime : nullptr, with_grad ? dbias : nullptr, st));
-  c->launches++;
-
   if (W > 1) {
-    if (with_grad) {
-      // dtxt of my text rows = sum over ranks of their contribution slot for me: what all_gather's backward
-      // (reduce-scatter SUM, torch functional.py:343-354) or the reverse ring (distributed_utils.py:75-77) delivers.
-      if (c->overlap_reduce) {
-        // only the contribution produced last (by rank r+1 in its final step) is still outstanding
-        CKI(siglip::launch_wait_flags(c->flags + 1 * kMaxWorld + (r + 1) % W, 1, s * static_cast<unsigned int>(W),
-                                      c->dbg_dev, st));
-        c->launches++;
-        CKI(siglip::launch_reduce_slots(dtxt, c->grad_bf16, c->final_ptrs_dev + (W > 2 ? 2 : 0), 2, chunk_elems,
-                                        c->num_sms, st));
-      } else {
-        if ((rc = signal_peers(c, 1, s * static_cast<unsigned int>(W), st))) return rc;
-        if ((rc = wait_peers(c, 1, s * static_cast<unsigned int>(W), st))) return rc;
-        CKI(siglip::launch_reduce_slots(dtxt, c->grad_bf16, c->reduce_ptrs_dev, W, chunk_elems, c->num_sms, st));
-      }
-      c->launches++;
+    if (c->overlap_reduce) {
+      // dtxt = (sum of the W-1 remote contributions, already local) + my own contribution: a local add
+      CKI(siglip::launch_reduce_slots(dtxt, c->grad_bf16, c->final_ptrs_dev, 2, chunk_elems, c->num_sms, st));
+    } else {
+      if ((rc = wait_peers(c, 1, base + static_cast<unsigned int>(W), st))) return rc;
+      CKI(siglip::launch_reduce_slots(dtxt, c->grad_bf16, c->reduce_ptrs_dev, W, chunk_elems, c->num_sms, st));
     }
-    if ((rc = signal_peers(c, 2, s, st))) return rc;
+    c->launches++;
+    if ((rc = signal_peers(c, 3, n, st))) return rc;
+  }
+  if (dt_prime != nullptr || dbias != nullptr) {
+    CKI(siglip::launch_scale_scalars(c->scalars + kSavedScalars, grad_out, dt_prime, dbias, st));
+    c->launches++;
   }
   CK(cudaGetLastError());
   return 0;
@@ -444,7 +505,7 @@ int step_impl(siglip_ctx* c, const void* img, const void* txt, const float* t_pr
 
 extern "C" {
 
-const char* siglip_version(void) { return "siglip_b200 0.1.0 sm_100a"; }
+const char* siglip_version(void) { return "siglip_b200 0.2.0 sm_100a"; }
 
 const char* siglip_last_error(void) { return g_last_error.c_str(); }
 
@@ -492,25 +553,26 @@ int siglip_ctx_create(siglip_ctx** out, int device, int rank, int world, int B, 
     total += bytes;
     return cudaMalloc(p, bytes);
   };
-  CK(alloc(reinterpret_cast<void**>(&c->G), static_cast<size_t>(c->Bp) * c->Bp * sizeof(__nv_bfloat16)));
   CK(alloc(reinterpret_cast<void**>(&c->g_diag), static_cast<size_t>(c->Bp) * sizeof(float)));
   CK(alloc(reinterpret_cast<void**>(&c->img16), chunk_elems * sizeof(__nv_bfloat16)));
-  CK(alloc(reinterpret_cast<void**>(&c->txt16), chunk_elems * sizeof(__nv_bfloat16)));
+  CK(alloc(reinterpret_cast<void**>(&c->txt16), chunk_elems * world * sizeof(__nv_bfloat16)));
   CK(alloc(reinterpret_cast<void**>(&c->partials), static_cast<size_t>(c->num_sms) * 4 * sizeof(double)));
   CK(alloc(reinterpret_cast<void**>(&c->flags), kFlagKinds * kMaxWorld * sizeof(unsigned int)));
-  CK(alloc(reinterpret_cast<void**>(&c->scalars), 8 * sizeof(float)));
+  CK(alloc(reinterpret_cast<void**>(&c->scalars), 16 * sizeof(float)));
   CK(cudaMemset(c->flags, 0, kFlagKinds * kMaxWorld * sizeof(unsigned int)));
   CK(cudaMemset(c->partials, 0, static_cast<size_t>(c->num_sms) * 4 * sizeof(double)));
   CK(cudaMemset(c->g_diag, 0, static_cast<size_t>(c->Bp) * sizeof(float)));
-  CK(cudaMemset(c->scalars, 0, 8 * sizeof(float)));
+  CK(cudaMemset(c->scalars, 0, 16 * sizeof(float)));
   if (world > 1) {
     CK(alloc(reinterpret_cast<void**>(&c->txt_all), chunk_elems * world * sizeof(__nv_bfloat16)));
     CK(alloc(reinterpret_cast<void**>(&c->slots), chunk_elems * world * sizeof(float)));
     CK(alloc(reinterpret_cast<void**>(&c->dimg_acc), chunk_elems * sizeof(float)));
     CK(alloc(reinterpret_cast<void**>(&c->dtxt_acc), chunk_elems * sizeof(float)));
-    CK(alloc(reinterpret_cast<void**>(&c->final_ptrs_dev), 4 * sizeof(float*)));
     CK(alloc(reinterpret_cast<void**>(&c->reduce_ptrs_dev), world * sizeof(float*)));
+    CK(alloc(reinterpret_cast<void**>(&c->final_ptrs_dev), 2 * sizeof(float*)));
     CK(alloc(reinterpret_cast<void**>(&c->signal_ptrs_dev), kFlagKinds * world * sizeof(unsigned int*)));
+    const float* fin[2] = {c->dtxt_acc, c->slots + rank * chunk_elems};
+    CK(cudaMemcpy(c->final_ptrs_dev, fin, sizeof(fin), cudaMemcpyHostToDevice));
   }
   CK(cudaHostAlloc(reinterpret_cast<void**>(&c->dbg_host), sizeof(DebugRecord), cudaHostAllocMapped));
   memset(c->dbg_host, 0, sizeof(DebugRecord));
@@ -519,6 +581,8 @@ int siglip_ctx_create(siglip_ctx** out, int device, int rank, int world, int B, 
   c->peer_slots[rank] = c->slots;
   c->peer_flags[rank] = c->flags;
   c->workspace_bytes = total;
+  int rc = ensure_g(c, 0);
+  if (rc) return rc;
   CK(cudaDeviceSynchronize());
   *out = c;
   return 0;
@@ -581,6 +645,20 @@ int siglip_ctx_export_handles(siglip_ctx* c, void* out_bytes, size_t capacity) {
   return 0;
 }
 
+static int publish_peer_tables(siglip_ctx* c) {
+  const size_t chunk_elems = static_cast<size_t>(c->B) * c->D;
+  std::vector<const float*> red(c->world);
+  for (int p = 0; p < c->world; ++p) red[p] = c->peer_slots[p] + c->rank * chunk_elems;
+  CK(cudaMemcpy(c->reduce_ptrs_dev, red.data(), c->world * sizeof(float*), cudaMemcpyHostToDevice));
+  std::vector<unsigned int*> sig(kFlagKinds * c->world);
+  for (int k = 0; k < kFlagKinds; ++k)
+    for (int p = 0; p < c->world; ++p)
+      sig[k * c->world + p] = c->peer_flags[p] + k * kMaxWorld + (c->loopback ? p : c->rank);
+  CK(cudaMemcpy(c->signal_ptrs_dev, sig.data(), sig.size() * sizeof(unsigned int*), cudaMemcpyHostToDevice));
+  c->peers_ready = true;
+  return 0;
+}
+
 int siglip_ctx_import_handles(siglip_ctx* c, const void* all_ranks_bytes, size_t bytes_per_rank) {
   if (c == nullptr || all_ranks_bytes == nullptr) return fail(SIGLIP_ERR_INVALID, "null argument");
   if (bytes_per_rank != sizeof(IpcBlob)) return fail(SIGLIP_ERR_INVALID, "bytes_per_rank != siglip_ctx_handle_bytes()");
@@ -602,34 +680,34 @@ int siglip_ctx_import_handles(siglip_ctx* c, const void* all_ranks_bytes, size_t
     c->peer_slots[p] = static_cast<float*>(ps);
     c->peer_flags[p] = static_cast<unsigned int*>(pf);
   }
-  const size_t chunk_elems = static_cast<size_t>(c->B) * c->D;
-  std::vector<const float*> red(c->world);
-  for (int p = 0; p < c->world; ++p) red[p] = c->peer_slots[p] + c->rank * chunk_elems;
-  CK(cudaMemcpy(c->reduce_ptrs_dev, red.data(), c->world * sizeof(float*), cudaMemcpyHostToDevice));
-  std::vector<unsigned int*> sig(kFlagKinds * c->world);
-  for (int k = 0; k < kFlagKinds; ++k)
-    for (int p = 0; p < c->world; ++p) sig[k * c->world + p] = c->peer_flags[p] + k * kMaxWorld + c->rank;
-  {
-    const int plast = (c->rank + 1) % c->world;   // the peer whose contribution for me is produced last
-    const float* fin[4] = {c->slots + c->rank * chunk_elems, c->peer_slots[plast] + c->rank * chunk_elems,
-                           c->dtxt_acc, c->peer_slots[plast] + c->rank * chunk_elems};
-    CK(cudaMemcpy(c->final_ptrs_dev, fin, sizeof(fin), cudaMemcpyHostToDevice));
-  }
-  CK(cudaMemcpy(c->signal_ptrs_dev, sig.data(), sig.size() * sizeof(unsigned int*), cudaMemcpyHostToDevice));
-  c->peers_ready = true;
-  return 0;
+  return publish_peer_tables(c);
+}
+
+int siglip_forward(siglip_ctx* c, const void* img, const void* txt, const float* t_prime, const float* bias,
+                   float* loss, int save_for_backward, void* cuda_stream) {
+  return forward_impl(c, img, txt, t_prime, bias, loss, save_for_backward != 0, static_cast<cudaStream_t>(cuda_stream));
+}
+
+unsigned long long siglip_ctx_saved_generation(const siglip_ctx* c) { return c ? c->gen : 0ull; }
+
+int siglip_backward(siglip_ctx* c, const void* img, const void* txt, const float* t_prime, const float* grad_out,
+                    void* dimg, void* dtxt, float* dt_prime, float* dbias, void* cuda_stream) {
+  return backward_impl(c, img, txt, t_prime, grad_out, dimg, dtxt, dt_prime, dbias,
+                       static_cast<cudaStream_t>(cuda_stream));
 }
 
 int siglip_fwd_bwd(siglip_ctx* c, const void* img, const void* txt, const float* t_prime, const float* bias,
                    float* loss, void* dimg, void* dtxt, float* dt_prime, float* dbias, void* cuda_stream) {
-  return step_impl(c, img, txt, t_prime, bias, loss, dimg, dtxt, dt_prime, dbias, true,
-                   static_cast<cudaStream_t>(cuda_stream));
+  if (dimg == nullptr || dtxt == nullptr || dt_prime == nullptr || dbias == nullptr)
+    return fail(SIGLIP_ERR_INVALID, "null gradient pointer");
+  int rc = siglip_forward(c, img, txt, t_prime, bias, loss, 1, cuda_stream);
+  if (rc) return rc;
+  return siglip_backward(c, img, txt, t_prime, nullptr, dimg, dtxt, dt_prime, dbias, cuda_stream);
 }
 
 int siglip_fwd(siglip_ctx* c, const void* img, const void* txt, const float* t_prime, const float* bias, float* loss,
                void* cuda_stream) {
-  return step_impl(c, img, txt, t_prime, bias, loss, nullptr, nullptr, nullptr, nullptr, false,
-                   static_cast<cudaStream_t>(cuda_stream));
+  return siglip_forward(c, img, txt, t_prime, bias, loss, 0, cuda_stream);
 }
 
 int siglip_fwd_bwd_host(siglip_ctx* c, const void* img_host, const void* txt_host, float t_prime, float bias,
@@ -653,8 +731,8 @@ int siglip_fwd_bwd_host(siglip_ctx* c, const void* img_host, const void* txt_hos
   CK(cudaMemcpyAsync(c->h_txt, txt_host, chunk_elems * sizeof(__nv_bfloat16), cudaMemcpyHostToDevice, st));
   const int saved_bf16 = c->grad_bf16;
   c->grad_bf16 = 0;  // the host entry returns fp32 gradients
-  int rc = step_impl(c, c->h_img, c->h_txt, c->scalars + 0, c->scalars + 1, c->scalars + 2, c->h_dimg, c->h_dtxt,
-                     c->scalars + 3, c->scalars + 4, true, st);
+  int rc = siglip_fwd_bwd(c, c->h_img, c->h_txt, c->scalars + 0, c->scalars + 1, c->scalars + 2, c->h_dimg, c->h_dtxt,
+                          c->scalars + 3, c->scalars + 4, st);
   c->grad_bf16 = saved_bf16;
   if (rc) return rc;
   float res[3];
@@ -696,28 +774,13 @@ int siglip_debug_loopback(siglip_ctx* c) {
   if (c == nullptr) return fail(SIGLIP_ERR_INVALID, "ctx is null");
   if (c->world == 1) return fail(SIGLIP_ERR_STATE, "loopback needs world > 1");
   CK(cudaSetDevice(c->device));
-  const size_t chunk_elems = static_cast<size_t>(c->B) * c->D;
   for (int p = 0; p < c->world; ++p) {
     c->peer_txt[p] = c->txt_all;
     c->peer_slots[p] = c->slots;
     c->peer_flags[p] = c->flags;
   }
-  std::vector<const float*> red(c->world);
-  for (int p = 0; p < c->world; ++p) red[p] = c->slots + c->rank * chunk_elems;
-  CK(cudaMemcpy(c->reduce_ptrs_dev, red.data(), c->world * sizeof(float*), cudaMemcpyHostToDevice));
-  std::vector<unsigned int*> sig(kFlagKinds * c->world);
-  for (int k = 0; k < kFlagKinds; ++k)
-    for (int p = 0; p < c->world; ++p) sig[k * c->world + p] = c->flags + k * kMaxWorld + p;
-  {
-    const int plast = (c->rank + 1) % c->world;   // the peer whose contribution for me is produced last
-    const float* fin[4] = {c->slots + c->rank * chunk_elems, c->peer_slots[plast] + c->rank * chunk_elems,
-                           c->dtxt_acc, c->peer_slots[plast] + c->rank * chunk_elems};
-    CK(cudaMemcpy(c->final_ptrs_dev, fin, sizeof(fin), cudaMemcpyHostToDevice));
-  }
-  CK(cudaMemcpy(c->signal_ptrs_dev, sig.data(), sig.size() * sizeof(unsigned int*), cudaMemcpyHostToDevice));
-  c->peers_ready = true;
-  c->loopback = true;
-  return 0;
+  c->loopback = true;   // every signal then raises the flag entry of EVERY rank in the local table
+  return publish_peer_tables(c);
 }
 
 int siglip_debug_set_text_chunk(siglip_ctx* c, int chunk, const void* txt_dev, void* cuda_stream) {
@@ -872,14 +935,16 @@ void siglip_ctx_destroy(siglip_ctx* c) {
   if (c == nullptr) return;
   cudaSetDevice(c->device);
   cudaDeviceSynchronize();
-  for (int p = 0; p < c->world; ++p) {
-    if (p == c->rank) continue;
-    if (c->peer_txt[p]) cudaIpcCloseMemHandle(c->peer_txt[p]);
-    if (c->peer_slots[p]) cudaIpcCloseMemHandle(c->peer_slots[p]);
-    if (c->peer_flags[p]) cudaIpcCloseMemHandle(c->peer_flags[p]);
+  if (!c->loopback) {
+    for (int p = 0; p < c->world; ++p) {
+      if (p == c->rank) continue;
+      if (c->peer_txt[p]) cudaIpcCloseMemHandle(c->peer_txt[p]);
+      if (c->peer_slots[p]) cudaIpcCloseMemHandle(c->peer_slots[p]);
+      if (c->peer_flags[p]) cudaIpcCloseMemHandle(c->peer_flags[p]);
+    }
   }
   cudaFree(c->txt_all);
-  cudaFree(c->G);
+  for (int k = 0; k < kMaxWorld; ++k) cudaFree(c->G[k]);
   cudaFree(c->g_diag);
   cudaFree(c->img16);
   cudaFree(c->txt16);

@@ -553,7 +553,7 @@ siglip_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_consta
         edge = (tile_m0 + C::kTileM > pr.M) || (tile_n0 + kTileN > pr.N);
         diag = p.own_chunk && (tile_m0 < tile_n0 + kTileN) && (tile_n0 < tile_m0 + C::kTileM);
       } else {
-        scale = t_exact * p.inv_b;
+        scale = t_exact * p.inv_b * (p.grad_out != nullptr ? *p.grad_out : 1.0f);
         fix = (pr.fix_vec != nullptr && row < pr.M) ? pr.fix_vec[row] : 0.f;
       }
 
@@ -705,15 +705,18 @@ siglip_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_consta
       for (; i + 3ull * nthreads < p.acc_n4; i += 4ull * nthreads) {
         float4 r0 = p.acc_remote[i], r1 = p.acc_remote[i + nthreads];
         float4 r2 = p.acc_remote[i + 2ull * nthreads], r3 = p.acc_remote[i + 3ull * nthreads];
-        const float4 a0 = p.acc_in[i], a1 = p.acc_in[i + nthreads];
-        const float4 a2 = p.acc_in[i + 2ull * nthreads], a3 = p.acc_in[i + 3ull * nthreads];
+        const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        const bool has_in = p.acc_in != nullptr;   // first contribution of a step: plain copy
+        const float4 a0 = has_in ? p.acc_in[i] : z4, a1 = has_in ? p.acc_in[i + nthreads] : z4;
+        const float4 a2 = has_in ? p.acc_in[i + 2ull * nthreads] : z4, a3 = has_in ? p.acc_in[i + 3ull * nthreads] : z4;
         p.acc_out[i] = make_float4(a0.x + r0.x, a0.y + r0.y, a0.z + r0.z, a0.w + r0.w);
         p.acc_out[i + nthreads] = make_float4(a1.x + r1.x, a1.y + r1.y, a1.z + r1.z, a1.w + r1.w);
         p.acc_out[i + 2ull * nthreads] = make_float4(a2.x + r2.x, a2.y + r2.y, a2.z + r2.z, a2.w + r2.w);
         p.acc_out[i + 3ull * nthreads] = make_float4(a3.x + r3.x, a3.y + r3.y, a3.z + r3.z, a3.w + r3.w);
       }
       for (; i < p.acc_n4; i += nthreads) {
-        const float4 rr = p.acc_remote[i], aa = p.acc_in[i];
+        const float4 rr = p.acc_remote[i];
+        const float4 aa = (p.acc_in != nullptr) ? p.acc_in[i] : make_float4(0.f, 0.f, 0.f, 0.f);
         p.acc_out[i] = make_float4(aa.x + rr.x, aa.y + rr.y, aa.z + rr.z, aa.w + rr.w);
       }
     }
@@ -752,6 +755,16 @@ __global__ void finalize_kernel(const double* __restrict__ partials, int nparts,
     if (loss) *loss = static_cast<float>(s0 * inv_b);
     if (dbias) *dbias = static_cast<float>(s1 * inv_b);
     if (dt_prime) *dt_prime = static_cast<float>(t * s2 * inv_b);
+  }
+}
+
+// backward of the two scalars: out = saved * grad_out
+__global__ void scale_scalars_kernel(const float* __restrict__ saved, const float* __restrict__ g, float* dt_prime,
+                                     float* dbias) {
+  const float s = (g != nullptr) ? *g : 1.0f;
+  if (threadIdx.x == 0) {
+    if (dt_prime) *dt_prime = saved[0] * s;
+    if (dbias) *dbias = saved[1] * s;
   }
 }
 
@@ -956,6 +969,11 @@ int launch_gemm(int cta_group, int mode, int stages, int mcast, const CUtensorMa
 int launch_finalize(const double* partials, int nparts, const float* t_prime, float inv_b, float* loss,
                     float* dt_prime, float* dbias, cudaStream_t stream) {
   finalize_kernel<<<1, 32, 0, stream>>>(partials, nparts, t_prime, inv_b, loss, dt_prime, dbias);
+  return static_cast<int>(cudaGetLastError());
+}
+
+int launch_scale_scalars(const float* saved, const float* g, float* dt_prime, float* dbias, cudaStream_t stream) {
+  scale_scalars_kernel<<<1, 32, 0, stream>>>(saved, g, dt_prime, dbias);
   return static_cast<int>(cudaGetLastError());
 }
 

@@ -38,6 +38,7 @@ struct KernelParams {
   const float* t_prime;
   const float* bias;
   float inv_b;  // 1 / per-rank batch (reference divides by the LOCAL batch, distributed_sigmoid_loss.py:47)
+  const float* grad_out;  // out kernel: optional device scalar multiplied into every gradient (autograd's grad_output)
   // epilogue of the "loss" kernel
   __nv_bfloat16* G;  // [Bp, ldg] bf16 sigma terms, diagonal zeroed; may be null when store_g == 0
   long long ldg;
@@ -93,6 +94,9 @@ int launch_finalize(const double* partials, int nparts, const float* t_prime, fl
                     float* dt_prime, float* dbias, cudaStream_t stream);
 
 int launch_zero_partials(double* partials, int nparts, cudaStream_t stream);
+
+// dt_prime = saved[0] * (*g), dbias = saved[1] * (*g)   (g == nullptr: 1)
+int launch_scale_scalars(const float* saved, const float* g, float* dt_prime, float* dbias, cudaStream_t stream);
 
 // dtxt[j, d] = sum_r slots[r][j, d]   (slots may be peer-mapped pointers; fp32; n = elements)
 int launch_reduce_slots(void* out, int out_bf16, const float* const* slots_dev, int nslots, size_t n, int num_sms,

@@ -106,12 +106,7 @@ class SigmoidLossEngine:
         (loss[1], dimg[B,D], dtxt[B,D], dt_prime[1], dbias[1]) for an upstream gradient of 1; scalars are fp32,
         dimg/dtxt are `grad_dtype` (fp32, or bf16 written directly by the kernel epilogue)."""
         self._check(img, txt)
-        if grad_dtype not in (torch.float32, torch.bfloat16):
-            raise RuntimeError("grad_dtype must be float32 or bfloat16")
-        want_bf16 = grad_dtype == torch.bfloat16
-        if want_bf16 != getattr(self, "_grad_bf16", False):
-            _capi.check(self._L.siglip_ctx_set_option(self._h, _capi.SIGLIP_OPT_GRAD_BF16, int(want_bf16)))
-            self._grad_bf16 = want_bf16
+        self._set_grad_dtype(grad_dtype)
         opts = dict(device=self.device, dtype=torch.float32)
         scal = torch.empty(3, **opts)                 # loss, dt', dbias in one allocation
         loss, dtp, db = scal[0:1], scal[1:2], scal[2:3]
@@ -122,6 +117,47 @@ class SigmoidLossEngine:
                                                bias.data_ptr(), loss.data_ptr(), dimg.data_ptr(), dtxt.data_ptr(),
                                                dtp.data_ptr(), db.data_ptr(), self._stream()))
         return loss, dimg, dtxt, dtp, db
+
+    # -- the two halves autograd uses ----------------------------------------------------------------------
+    @property
+    def saved_generation(self) -> int:
+        return int(self._L.siglip_ctx_saved_generation(self._h))
+
+    def forward(self, img: torch.Tensor, txt: torch.Tensor, t_prime: torch.Tensor, bias: torch.Tensor,
+                save_for_backward: bool) -> torch.Tensor:
+        """The W loss kernels. Returns loss[1] (fp32). With save_for_backward the context keeps the sigma operands."""
+        self._check(img, txt)
+        loss = torch.empty(1, device=self.device, dtype=torch.float32)
+        with torch.cuda.device(self.device):
+            _capi.check(self._L.siglip_forward(self._h, img.data_ptr(), txt.data_ptr(), t_prime.data_ptr(),
+                                               bias.data_ptr(), loss.data_ptr(), int(bool(save_for_backward)),
+                                               self._stream()))
+        return loss
+
+    def backward(self, img: torch.Tensor, txt: torch.Tensor, t_prime: torch.Tensor, grad_out: Optional[torch.Tensor],
+                 grad_dtype: torch.dtype = torch.float32):
+        """The W gradient kernels on the state saved by the last forward(save_for_backward=True); every gradient is
+        multiplied by grad_out (1-element fp32 device tensor, or None for 1) inside the kernel epilogues.
+        Returns (dimg, dtxt) in grad_dtype and (dt_prime, dbias) as fp32 [1]."""
+        self._check(img, txt)
+        self._set_grad_dtype(grad_dtype)
+        scal = torch.empty(2, device=self.device, dtype=torch.float32)
+        dimg = torch.empty(self.batch, self.dim, device=self.device, dtype=grad_dtype)
+        dtxt = torch.empty(self.batch, self.dim, device=self.device, dtype=grad_dtype)
+        with torch.cuda.device(self.device):
+            _capi.check(self._L.siglip_backward(self._h, img.data_ptr(), txt.data_ptr(), t_prime.data_ptr(),
+                                                grad_out.data_ptr() if grad_out is not None else None,
+                                                dimg.data_ptr(), dtxt.data_ptr(), scal[0:1].data_ptr(),
+                                                scal[1:2].data_ptr(), self._stream()))
+        return dimg, dtxt, scal[0:1], scal[1:2]
+
+    def _set_grad_dtype(self, grad_dtype: torch.dtype) -> None:
+        if grad_dtype not in (torch.float32, torch.bfloat16):
+            raise RuntimeError("grad_dtype must be float32 or bfloat16")
+        want_bf16 = grad_dtype == torch.bfloat16
+        if want_bf16 != getattr(self, "_grad_bf16", False):
+            _capi.check(self._L.siglip_ctx_set_option(self._h, _capi.SIGLIP_OPT_GRAD_BF16, int(want_bf16)))
+            self._grad_bf16 = want_bf16
 
     def scale(self, src: torch.Tensor, g: torch.Tensor) -> torch.Tensor:
         """src * g with g a 1-element fp32 device tensor (grad_output): one fused pass of the C library."""
@@ -183,8 +219,10 @@ class SigmoidLossEngine:
 
 
 class _SigmoidLossFn(torch.autograd.Function):
-    """loss = sum_chunks(-logsigmoid(labels * (img @ txt_chunk.T * exp(t') + b))).sum() / B, with the four
-    gradients produced in the same fused pass: backward only scales by the upstream scalar."""
+    """loss = sum_chunks(-logsigmoid(labels * (img @ txt_chunk.T * exp(t') + b))).sum() / B.
+    forward  = the loss kernels (the sigma operands stay in the engine when a gradient is needed),
+    backward = the gradient kernels, with grad_output folded into their epilogues (the four gradients
+    depend on the logits and a scalar only)."""
 
     @staticmethod
     def forward(ctx, img, txt, t_prime, bias, engine: SigmoidLossEngine):
@@ -193,30 +231,35 @@ class _SigmoidLossFn(torch.autograd.Function):
         txt_b = txt.detach().to(torch.bfloat16).contiguous()
         tp = t_prime.detach().to(device=img.device, dtype=torch.float32).reshape(1)
         b = bias.detach().to(device=img.device, dtype=torch.float32).reshape(1)
-        ctx.in_meta = (img.dtype, txt.dtype, t_prime.dtype, bias.dtype, t_prime.shape, bias.shape,
-                       t_prime.device, bias.device)
+        loss = engine.forward(img_b, txt_b, tp, b, need_grad)
         if need_grad:
-            # gradients in the dtype autograd would return for these inputs: bf16 straight from the kernel epilogue
-            gdt = torch.bfloat16 if (img.dtype == torch.bfloat16 and txt.dtype == torch.bfloat16) else torch.float32
-            loss, dimg, dtxt, dtp, db = engine.fwd_bwd(img_b, txt_b, tp, b, gdt)
-            ctx.save_for_backward(dimg, dtxt, dtp, db)
+            ctx.save_for_backward(img_b, txt_b, tp, b)
             ctx.engine = engine
-        else:
-            loss = engine.fwd(img_b, txt_b, tp, b)
+            ctx.gen = engine.saved_generation
+            ctx.in_meta = (img.dtype, txt.dtype, t_prime.dtype, bias.dtype, t_prime.shape, bias.shape,
+                           t_prime.device, bias.device)
         # reference result dtype: promote(input dtype, fp32 labels) (distributed_sigmoid_loss.py:28-32)
         out_dtype = torch.promote_types(img.dtype, torch.float32)
         return loss.reshape(()).to(out_dtype)
 
     @staticmethod
     def backward(ctx, grad_out):
-        dimg, dtxt, dtp, db = ctx.saved_tensors
-        idt, tdt, pdt, bdt, pshape, bshape, pdev, bdev = ctx.in_meta
-        g = grad_out.detach().to(torch.float32).reshape(1).contiguous()
+        img_b, txt_b, tp, b = ctx.saved_tensors
         eng = ctx.engine
-        gi = eng.scale(dimg, g).to(idt) if ctx.needs_input_grad[0] else None
-        gt = eng.scale(dtxt, g).to(tdt) if ctx.needs_input_grad[1] else None
-        gp = (dtp * g).reshape(pshape).to(device=pdev, dtype=pdt) if ctx.needs_input_grad[2] else None
-        gb = (db * g).reshape(bshape).to(device=bdev, dtype=bdt) if ctx.needs_input_grad[3] else None
+        idt, tdt, pdt, bdt, pshape, bshape, pdev, bdev = ctx.in_meta
+        if eng.saved_generation != ctx.gen:
+            # another forward of the same module ran in between: rebuild the saved state (every rank takes this branch
+            # together, so the collective stays matched)
+            eng.forward(img_b, txt_b, tp, b, True)
+            ctx.gen = eng.saved_generation
+        g = grad_out.detach().to(torch.float32).reshape(1).contiguous()
+        # gradients in the dtype autograd would return for these inputs: bf16 straight from the kernel epilogue
+        gdt = torch.bfloat16 if (idt == torch.bfloat16 and tdt == torch.bfloat16) else torch.float32
+        dimg, dtxt, dtp, db = eng.backward(img_b, txt_b, tp, g, gdt)
+        gi = dimg.to(idt) if ctx.needs_input_grad[0] else None
+        gt = dtxt.to(tdt) if ctx.needs_input_grad[1] else None
+        gp = dtp.reshape(pshape).to(device=pdev, dtype=pdt) if ctx.needs_input_grad[2] else None
+        gb = db.reshape(bshape).to(device=bdev, dtype=bdt) if ctx.needs_input_grad[3] else None
         return gi, gt, gp, gb, None
 
 

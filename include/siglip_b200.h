@@ -56,8 +56,8 @@ int siglip_device_count(void);
 /*
  * Create the per-process context: replaces DDPSigmoidLoss.__init__ (distributed_sigmoid_loss.py:9-15) —
  * `B` is its gpu_batch_size, `rank`/`world` what dist.get_rank()/get_world_size() return at :37-38.
- * Allocates the workspaces (gathered text [world*B, D] bf16, sigma operand [Bp, Bp] bf16, per-owner dtxt
- * slots [world][B, D] fp32, reduction partials, flags). `device` is the CUDA device ordinal.
+ * Allocates the workspaces (gathered text [world*B, D] bf16, per-owner dtxt slots [world][B, D] fp32, fp16 operand
+ * copies, reduction partials, flags; the [Bp, Bp] 16-bit sigma operands — one per text chunk — on first use). `device` is the CUDA device ordinal.
  */
 int siglip_ctx_create(siglip_ctx** out, int device, int rank, int world, int B, int D);
 
@@ -78,7 +78,7 @@ int siglip_ctx_export_handles(siglip_ctx* ctx, void* out_bytes, size_t capacity)
 int siglip_ctx_import_handles(siglip_ctx* ctx, const void* all_ranks_bytes, size_t bytes_per_rank);
 
 /*
- * One training step of the loss: replaces DDPSigmoidLoss.forward (distributed_sigmoid_loss.py:17-48) AND
+ * One training step of the loss (siglip_forward + siglip_backward with upstream gradient 1): replaces DDPSigmoidLoss.forward (distributed_sigmoid_loss.py:17-48) AND
  * the autograd backward of it, i.e. loss plus the four gradients for upstream grad 1:
  *   loss      [1]    = (1/B) sum_ij softplus(-y_ij z_ij)
  *   dimg      [B,D]  = dloss/dimg           (this rank's loss only)
@@ -97,7 +97,25 @@ int siglip_fwd_bwd(siglip_ctx* ctx, const void* img, const void* txt, const floa
 int siglip_scale(siglip_ctx* ctx, const void* src, void* dst, size_t nbytes, int is_bf16, const float* g,
                  void* cuda_stream);
 
-/* Forward only (torch.no_grad / evaluation): same collective contract, no gradient work. */
+/*
+ * The same step as two calls, the shape autograd wants:
+ *   siglip_forward  — the W loss kernels; with save_for_backward != 0 it also keeps, inside the context, the sigma
+ *                     operands, the fp16 operand copies and dt'/dbias that the backward needs (replaces the autograd
+ *                     graph the reference records at distributed_sigmoid_loss.py:22-33);
+ *   siglip_backward — the W gradient kernels on that saved state, every gradient multiplied by the upstream scalar
+ *                     `grad_out` (device pointer; NULL = 1) in the kernel epilogue (replaces the graph replay,
+ *                     SURVEY.md §3.2). `img` / `txt` must be the buffers given to the forward.
+ * Both are collectives over the context's world. siglip_ctx_saved_generation() identifies the saved state (0 = none):
+ * a backward must follow the forward that produced the generation it expects (the Python mirror re-runs the forward if
+ * another forward intervened).
+ */
+int siglip_forward(siglip_ctx* ctx, const void* img, const void* txt, const float* t_prime, const float* bias,
+                   float* loss, int save_for_backward, void* cuda_stream);
+int siglip_backward(siglip_ctx* ctx, const void* img, const void* txt, const float* t_prime, const float* grad_out,
+                    void* dimg, void* dtxt, float* dt_prime, float* dbias, void* cuda_stream);
+unsigned long long siglip_ctx_saved_generation(const siglip_ctx* ctx);
+
+/* Forward only (torch.no_grad / evaluation): siglip_forward with save_for_backward = 0. */
 int siglip_fwd(siglip_ctx* ctx, const void* img, const void* txt, const float* t_prime, const float* bias,
                float* loss, void* cuda_stream);
 

@@ -363,6 +363,42 @@ def test_bf16_gradient_outputs_and_fused_scale():
     assert torch.equal(outs[1], outs[0].to(torch.bfloat16))
 
 
+def test_split_forward_backward_and_generation_guard():
+    """siglip_forward / siglip_backward: grad_out folded into the epilogues; a backward after an intervening forward of
+    the same module recomputes the saved state instead of using stale sigma operands."""
+    from distributed_sigmoid_loss_b200 import DDPSigmoidLoss
+
+    B, D = 768, 256
+    img, txt = _synth(B, D)
+    img2, txt2 = _synth(B, D, 5)
+    eng = _engine(B, D, 2)
+    tp, bias = _scal(math.log(10.0)), _scal(-10.0)
+    _, dimg, dtxt, dtp, db = eng.fwd_bwd(img, txt, tp, bias)
+    eng.forward(img, txt, tp, bias, True)
+    g = _scal(-1.75)
+    d2, t2, p2, b2 = eng.backward(img, txt, tp, g)
+    torch.cuda.synchronize()
+    _check("dimg * g", d2, dimg * -1.75, tol=1e-6)
+    _check("dtxt * g", t2, dtxt * -1.75, tol=1e-6)
+    _check("dt' * g", p2, float(dtp) * -1.75, tol=1e-6)
+    _check("dbias * g", b2, float(db) * -1.75, tol=1e-6)
+    eng.close()
+    # two graphs on one module, backward in reverse order
+    mod = DDPSigmoidLoss(B).to(_dev())
+    a1, a2 = img.clone().requires_grad_(True), img2.clone().requires_grad_(True)
+    l1 = mod(a1, txt)
+    l2 = mod(a2, txt2)
+    l1.backward()
+    l2.backward()
+    e1 = _engine(B, D, 2)
+    _, r1, _, _, _ = e1.fwd_bwd(img, txt, _scal(float(mod.t_prime)), _scal(float(mod.bias)))
+    _, r2, _, _, _ = e1.fwd_bwd(img2, txt2, _scal(float(mod.t_prime)), _scal(float(mod.bias)))
+    torch.cuda.synchronize()
+    _check("graph 1 dimg", a1.grad.float(), r1, tol=4e-3)
+    _check("graph 2 dimg", a2.grad.float(), r2, tol=4e-3)
+    e1.close()
+
+
 def test_kernel_launch_accounting():
     B, D = 512, 128
     img, txt = _synth(B, D)
@@ -372,7 +408,7 @@ def test_kernel_launch_accounting():
     eng.set_option(_capi.SIGLIP_OPT_KERNEL_TIMING, 1)
     n0 = eng.launch_count
     eng.fwd_bwd(img, txt, _scal(1.0), _scal(-5.0))
-    assert eng.launch_count - n0 == 4          # zero partials, loss kernel, gradient kernel, finalize
+    assert eng.launch_count - n0 == 5          # zero partials, loss kernel, finalize | gradient kernel, scalar scale
     lm, ln, gm, gn = eng.kernel_times()
     assert ln == 1 and gn == 1 and lm > 0 and gm > 0
     eng.close()
