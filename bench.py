@@ -300,6 +300,9 @@ def run_ours(args):
                                    "(BASELINE.json headline shape; at N=1 the single-chunk case)",
                        "global_batch": B * W, "batch_per_rank": B, "dim": D, "world": W,
                        "parallelism": f"dp{W}", "cta_group": args.cta_group,
+                       "scaling_note": "weak scaling: B/rank fixed, each rank scores W = n_gpus text chunks, so per-rank work "
+                                       "grows with N and pairs/s per GPU falls as 1/N at perfect scaling; compare "
+                                       "tflops_per_gpu across N (FLOP-normalised efficiency = W*t(1)/t(W))",
                        "l2": "no explicit flush: each step streams >1 GiB (bf16 sigma operand) through the 126 MB L2",
                        "api": "DDPSigmoidLoss.forward + loss.backward() (torch autograd over the C ABI)"},
             "loss": float(loss),

@@ -762,6 +762,26 @@ int siglip_ctx_kernel_times(siglip_ctx* c, double* loss_ms, int* loss_launches, 
     CK(cudaEventElapsedTime(&ms, c->ev_grad[i], c->ev_grad[i + 1]));
     tg += ms;
   }
+  if (getenv("SIGLIP_DEBUG_PRINT_TIMES")) {  // per-launch durations of the last W loss / gradient launches
+    std::string s = "[kernel times rank " + std::to_string(c->rank) + "] loss:";
+    char b[32];
+    const size_t nl = c->ev_loss_used / 2, ng = c->ev_grad_used / 2;
+    for (size_t i = (nl > (size_t)c->world ? nl - c->world : 0); i < nl; ++i) {
+      float ms = 0.f;
+      cudaEventElapsedTime(&ms, c->ev_loss[2 * i], c->ev_loss[2 * i + 1]);
+      snprintf(b, sizeof(b), " %.3f", ms);
+      s += b;
+    }
+    s += " | grad:";
+    for (size_t i = (ng > (size_t)c->world ? ng - c->world : 0); i < ng; ++i) {
+      float ms = 0.f;
+      cudaEventElapsedTime(&ms, c->ev_grad[2 * i], c->ev_grad[2 * i + 1]);
+      snprintf(b, sizeof(b), " %.3f", ms);
+      s += b;
+    }
+    printf("%s\n", s.c_str());
+    fflush(stdout);
+  }
   if (loss_ms) *loss_ms = tl;
   if (grad_ms) *grad_ms = tg;
   if (loss_launches) *loss_launches = static_cast<int>(c->ev_loss_used / 2);

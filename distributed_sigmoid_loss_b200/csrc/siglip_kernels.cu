@@ -90,31 +90,38 @@ __device__ __forceinline__ double warp_sum(double v) {
   return v;
 }
 
-// Bounded acquire-spin on a flag written by a peer GPU (st.release.sys): >= value, or trap after 20 s.
+// Bounded wait of the two auxiliary warps (64 threads) of a CTA on a flag written by a peer GPU (st.release.sys):
+// ONE thread per CTA polls (acquire, system scope) with a back-off — thousands of threads hammering one L2 line slowed
+// the MMA operand traffic of the whole kernel — then the 64 threads meet on a named barrier. Traps after 20 s.
 __device__ __forceinline__ void wait_peer_flag(const volatile unsigned int* flag, unsigned int value, DebugRecord* dbg,
                                                unsigned int site) {
-  uint64_t t0 = 0;
-  uint32_t spins = 0;
-  while (true) {
-    unsigned int v;
-    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
-    if (v >= value) break;
-    if ((++spins & 0xffu) == 0) {
-      const uint64_t now = globaltimer_ns();
-      if (t0 == 0) t0 = now;
-      if (now - t0 > 20000000000ull) {
-        if (dbg != nullptr && (threadIdx.x & 31) == 0) {
-          dbg->block = blockIdx.x;
-          dbg->thread = threadIdx.x;
-          dbg->aux0 = v;
-          dbg->aux1 = value;
-          dbg->code = site;
-          __threadfence_system();
+  if (threadIdx.x == kAllocWarp * 32) {
+    uint64_t t0 = 0;
+    uint32_t spins = 0;
+    while (true) {
+      unsigned int v;
+      asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
+      if (v >= value) break;
+      __nanosleep(200);
+      if ((++spins & 0xffu) == 0) {
+        const uint64_t now = globaltimer_ns();
+        if (t0 == 0) t0 = now;
+        if (now - t0 > 20000000000ull) {
+          if (dbg != nullptr) {
+            dbg->block = blockIdx.x;
+            dbg->thread = threadIdx.x;
+            dbg->aux0 = v;
+            dbg->aux1 = value;
+            dbg->code = site;
+            __threadfence_system();
+          }
+          __trap();
         }
-        __trap();
       }
     }
+    __threadfence();  // order the peer data reads of the other 63 threads after the observed flag
   }
+  asm volatile("bar.sync 2, 64;" ::: "memory");
 }
 
 struct TileCoord {
