@@ -33,6 +33,8 @@ EXPORTED_SYMBOLS = (
     "siglip_fwd",
     "siglip_fwd_bwd_host",
     "siglip_scale",
+    "siglip_normalize_fwd",
+    "siglip_normalize_bwd",
     "siglip_ctx_kernel_times",
     "siglip_ctx_launch_count",
     "siglip_debug_gemm",
@@ -117,6 +119,10 @@ def lib() -> ctypes.CDLL:
     L.siglip_fwd.restype = ci
     L.siglip_fwd_bwd_host.argtypes = [vp, vp, vp, ctypes.c_float, ctypes.c_float, vp, vp, vp, vp, vp, vp]
     L.siglip_fwd_bwd_host.restype = ci
+    L.siglip_normalize_fwd.argtypes = [vp, vp, ci, vp, vp, vp]
+    L.siglip_normalize_fwd.restype = ci
+    L.siglip_normalize_bwd.argtypes = [vp, vp, ci, vp, vp, ci, vp, vp]
+    L.siglip_normalize_bwd.restype = ci
     L.siglip_scale.argtypes = [vp, vp, vp, cs, ci, vp, vp]
     L.siglip_scale.restype = ci
     L.siglip_ctx_kernel_times.argtypes = [vp, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ci),

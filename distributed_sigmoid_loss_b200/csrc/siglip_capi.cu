@@ -821,6 +821,33 @@ int siglip_debug_get_slot(siglip_ctx* c, int chunk, float* out_dev, void* cuda_s
   return 0;
 }
 
+int siglip_normalize_fwd(siglip_ctx* c, const void* x, int in_bf16, void* xhat_bf16, float* inv_norm,
+                         void* cuda_stream) {
+  if (c == nullptr || x == nullptr || xhat_bf16 == nullptr || inv_norm == nullptr)
+    return fail(SIGLIP_ERR_INVALID, "null argument");
+  if ((reinterpret_cast<uintptr_t>(x) & 15u) || (reinterpret_cast<uintptr_t>(xhat_bf16) & 15u))
+    return fail(SIGLIP_ERR_INVALID, "buffers must be 16-byte aligned");
+  CK(cudaSetDevice(c->device));
+  CKI(siglip::launch_normalize_fwd(x, in_bf16, static_cast<__nv_bfloat16*>(xhat_bf16), inv_norm, c->B, c->D,
+                                   c->num_sms, static_cast<cudaStream_t>(cuda_stream)));
+  c->launches++;
+  return 0;
+}
+
+int siglip_normalize_bwd(siglip_ctx* c, const void* x, int in_bf16, const float* inv_norm, const void* dxhat,
+                         int grad_bf16, void* dx, void* cuda_stream) {
+  if (c == nullptr || x == nullptr || inv_norm == nullptr || dxhat == nullptr || dx == nullptr)
+    return fail(SIGLIP_ERR_INVALID, "null argument");
+  if ((reinterpret_cast<uintptr_t>(x) & 15u) || (reinterpret_cast<uintptr_t>(dxhat) & 15u) ||
+      (reinterpret_cast<uintptr_t>(dx) & 15u))
+    return fail(SIGLIP_ERR_INVALID, "buffers must be 16-byte aligned");
+  CK(cudaSetDevice(c->device));
+  CKI(siglip::launch_normalize_bwd(x, in_bf16, inv_norm, dxhat, grad_bf16, dx, c->B, c->D, c->num_sms,
+                                   static_cast<cudaStream_t>(cuda_stream)));
+  c->launches++;
+  return 0;
+}
+
 int siglip_scale(siglip_ctx* c, const void* src, void* dst, size_t nbytes, int is_bf16, const float* g,
                  void* cuda_stream) {
   if (c == nullptr || src == nullptr || dst == nullptr || g == nullptr) return fail(SIGLIP_ERR_INVALID, "null argument");

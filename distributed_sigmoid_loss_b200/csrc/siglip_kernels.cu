@@ -859,6 +859,102 @@ __global__ void wait_flags_kernel(const volatile unsigned int* flags, int n, uns
   }
 }
 
+// -------------------------------------------------------------------------------------------------
+// L2 normalisation fused around the loss (the step the reference's callers run right before it,
+// test_distributed_sigmoid_loss.py:99-101). One warp per row; HBM-bound: coalesced 16-byte accesses, fp32 math.
+// -------------------------------------------------------------------------------------------------
+template <bool kInBf16>
+__device__ __forceinline__ void load8(const void* base, size_t idx8, float (&v)[8]) {
+  if constexpr (kInBf16) {
+    const uint4 w = reinterpret_cast<const uint4*>(base)[idx8];
+    const uint32_t u[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      v[2 * q] = __uint_as_float(u[q] << 16);
+      v[2 * q + 1] = __uint_as_float(u[q] & 0xffff0000u);
+    }
+  } else {
+    const float4 a = reinterpret_cast<const float4*>(base)[2 * idx8];
+    const float4 b = reinterpret_cast<const float4*>(base)[2 * idx8 + 1];
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
+    v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+  }
+}
+
+template <bool kOutBf16>
+__device__ __forceinline__ void store8(void* base, size_t idx8, const float (&v)[8]) {
+  if constexpr (kOutBf16) {
+    reinterpret_cast<uint4*>(base)[idx8] = make_uint4(pack_16x2<false>(v[0], v[1]), pack_16x2<false>(v[2], v[3]),
+                                                      pack_16x2<false>(v[4], v[5]), pack_16x2<false>(v[6], v[7]));
+  } else {
+    reinterpret_cast<float4*>(base)[2 * idx8] = make_float4(v[0], v[1], v[2], v[3]);
+    reinterpret_cast<float4*>(base)[2 * idx8 + 1] = make_float4(v[4], v[5], v[6], v[7]);
+  }
+}
+
+__device__ __forceinline__ float warp_sum_f(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// xhat[r, :] = bf16(x[r, :] / max(||x[r, :]||, eps)),  inv_norm[r] = 1 / max(||x||, eps)      (F.normalize, eps 1e-12)
+template <bool kInBf16>
+__global__ void normalize_fwd_kernel(const void* __restrict__ x, __nv_bfloat16* __restrict__ xhat,
+                                     float* __restrict__ inv_norm, int rows, int d8) {
+  const int warps_per_block = blockDim.x >> 5;
+  const int lane = threadIdx.x & 31;
+  for (int r = blockIdx.x * warps_per_block + (threadIdx.x >> 5); r < rows; r += gridDim.x * warps_per_block) {
+    const size_t row8 = static_cast<size_t>(r) * d8;
+    float ss = 0.f;
+    for (int c = lane; c < d8; c += 32) {
+      float v[8];
+      load8<kInBf16>(x, row8 + c, v);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) ss = fmaf(v[e], v[e], ss);
+    }
+    ss = warp_sum_f(ss);
+    const float inv = 1.0f / fmaxf(sqrtf(ss), 1e-12f);
+    if (lane == 0) inv_norm[r] = inv;
+    for (int c = lane; c < d8; c += 32) {
+      float v[8];
+      load8<kInBf16>(x, row8 + c, v);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) v[e] *= inv;
+      store8<true>(xhat, row8 + c, v);
+    }
+  }
+}
+
+// dx = inv * (dxhat - xhat * <xhat, dxhat>) with xhat = x * inv recomputed in fp32 from the raw input
+template <bool kInBf16, bool kGradBf16>
+__global__ void normalize_bwd_kernel(const void* __restrict__ x, const float* __restrict__ inv_norm,
+                                     const void* __restrict__ dxhat, void* __restrict__ dx, int rows, int d8) {
+  const int warps_per_block = blockDim.x >> 5;
+  const int lane = threadIdx.x & 31;
+  for (int r = blockIdx.x * warps_per_block + (threadIdx.x >> 5); r < rows; r += gridDim.x * warps_per_block) {
+    const size_t row8 = static_cast<size_t>(r) * d8;
+    const float inv = inv_norm[r];
+    float dot = 0.f;
+    for (int c = lane; c < d8; c += 32) {
+      float v[8], g[8];
+      load8<kInBf16>(x, row8 + c, v);
+      load8<kGradBf16>(dxhat, row8 + c, g);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) dot = fmaf(v[e] * inv, g[e], dot);
+    }
+    dot = warp_sum_f(dot);
+    for (int c = lane; c < d8; c += 32) {
+      float v[8], g[8], o[8];
+      load8<kInBf16>(x, row8 + c, v);
+      load8<kGradBf16>(dxhat, row8 + c, g);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) o[e] = inv * (g[e] - v[e] * inv * dot);
+      store8<kInBf16>(dx, row8 + c, o);
+    }
+  }
+}
+
 template <int kCG, int kMode, int kStages, int kMC>
 int launch_impl(const CUtensorMap* tmA0, const CUtensorMap* tmB0, const CUtensorMap* tmA1, const CUtensorMap* tmB1,
                 const CUtensorMap* tmG, const KernelParams& p, int num_sms, cudaStream_t stream) {
@@ -993,6 +1089,30 @@ int launch_zero_partials(double* partials, int nparts, cudaStream_t stream) {
 int launch_reduce_slots(void* out, int out_bf16, const float* const* slots_dev, int nslots, size_t n, int num_sms,
                         cudaStream_t stream) {
   reduce_slots_kernel<<<num_sms * 4, 256, 0, stream>>>(out, out_bf16, slots_dev, nslots, n / 4);
+  return static_cast<int>(cudaGetLastError());
+}
+
+int launch_normalize_fwd(const void* x, int in_bf16, __nv_bfloat16* xhat, float* inv_norm, int rows, int D,
+                         int num_sms, cudaStream_t stream) {
+  const int grid = num_sms * 8, block = 256;
+  if (in_bf16)
+    normalize_fwd_kernel<true><<<grid, block, 0, stream>>>(x, xhat, inv_norm, rows, D / 8);
+  else
+    normalize_fwd_kernel<false><<<grid, block, 0, stream>>>(x, xhat, inv_norm, rows, D / 8);
+  return static_cast<int>(cudaGetLastError());
+}
+
+int launch_normalize_bwd(const void* x, int in_bf16, const float* inv_norm, const void* dxhat, int grad_bf16, void* dx,
+                         int rows, int D, int num_sms, cudaStream_t stream) {
+  const int grid = num_sms * 8, block = 256;
+  if (in_bf16 && grad_bf16)
+    normalize_bwd_kernel<true, true><<<grid, block, 0, stream>>>(x, inv_norm, dxhat, dx, rows, D / 8);
+  else if (in_bf16)
+    normalize_bwd_kernel<true, false><<<grid, block, 0, stream>>>(x, inv_norm, dxhat, dx, rows, D / 8);
+  else if (grad_bf16)
+    normalize_bwd_kernel<false, true><<<grid, block, 0, stream>>>(x, inv_norm, dxhat, dx, rows, D / 8);
+  else
+    normalize_bwd_kernel<false, false><<<grid, block, 0, stream>>>(x, inv_norm, dxhat, dx, rows, D / 8);
   return static_cast<int>(cudaGetLastError());
 }
 

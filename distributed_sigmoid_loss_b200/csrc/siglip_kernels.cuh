@@ -102,6 +102,13 @@ int launch_scale_scalars(const float* saved, const float* g, float* dt_prime, fl
 int launch_reduce_slots(void* out, int out_bf16, const float* const* slots_dev, int nslots, size_t n, int num_sms,
                         cudaStream_t stream);
 
+// xhat = bf16(x / max(||x||, 1e-12)) row-wise, inv_norm[r] = 1 / max(||x_r||, 1e-12); x is fp32 or bf16 [rows, D]
+int launch_normalize_fwd(const void* x, int in_bf16, __nv_bfloat16* xhat, float* inv_norm, int rows, int D,
+                         int num_sms, cudaStream_t stream);
+// dx = inv_norm * (dxhat - xhat <xhat, dxhat>), xhat recomputed in fp32 from x; dx has x's dtype
+int launch_normalize_bwd(const void* x, int in_bf16, const float* inv_norm, const void* dxhat, int grad_bf16, void* dx,
+                         int rows, int D, int num_sms, cudaStream_t stream);
+
 // dst = src * (*g) over nbytes (multiple of 16) of fp32 or bf16 data
 int launch_scale(const void* src, void* dst, int is_bf16, const float* g, size_t nbytes, int num_sms,
                  cudaStream_t stream);

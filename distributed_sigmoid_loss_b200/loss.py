@@ -159,6 +159,28 @@ class SigmoidLossEngine:
             _capi.check(self._L.siglip_ctx_set_option(self._h, _capi.SIGLIP_OPT_GRAD_BF16, int(want_bf16)))
             self._grad_bf16 = want_bf16
 
+    def normalize_fwd(self, x: torch.Tensor):
+        """F.normalize(x, dim=1) fused with the bf16 rounding the loss kernel needs: returns (xhat bf16 [B, D],
+        inv_norm fp32 [B]). x: fp32 or bf16 [B, D] contiguous."""
+        if tuple(x.shape) != (self.batch, self.dim) or x.dtype not in (torch.float32, torch.bfloat16) or \
+                not x.is_contiguous() or x.device != self.device:
+            raise RuntimeError(f"normalize_fwd expects a contiguous fp32/bf16 [{self.batch}, {self.dim}] tensor on {self.device}")
+        xhat = torch.empty(self.batch, self.dim, device=self.device, dtype=torch.bfloat16)
+        inv = torch.empty(self.batch, device=self.device, dtype=torch.float32)
+        with torch.cuda.device(self.device):
+            _capi.check(self._L.siglip_normalize_fwd(self._h, x.data_ptr(), int(x.dtype == torch.bfloat16),
+                                                     xhat.data_ptr(), inv.data_ptr(), self._stream()))
+        return xhat, inv
+
+    def normalize_bwd(self, x: torch.Tensor, inv: torch.Tensor, dxhat: torch.Tensor) -> torch.Tensor:
+        """Backward of normalize_fwd: dx = inv * (dxhat - xhat <xhat, dxhat>), in x's dtype."""
+        dx = torch.empty_like(x)
+        with torch.cuda.device(self.device):
+            _capi.check(self._L.siglip_normalize_bwd(self._h, x.data_ptr(), int(x.dtype == torch.bfloat16),
+                                                     inv.data_ptr(), dxhat.data_ptr(),
+                                                     int(dxhat.dtype == torch.bfloat16), dx.data_ptr(), self._stream()))
+        return dx
+
     def scale(self, src: torch.Tensor, g: torch.Tensor) -> torch.Tensor:
         """src * g with g a 1-element fp32 device tensor (grad_output): one fused pass of the C library."""
         if src.dtype not in (torch.float32, torch.bfloat16) or not src.is_contiguous():
@@ -222,18 +244,35 @@ class _SigmoidLossFn(torch.autograd.Function):
     """loss = sum_chunks(-logsigmoid(labels * (img @ txt_chunk.T * exp(t') + b))).sum() / B.
     forward  = the loss kernels (the sigma operands stay in the engine when a gradient is needed),
     backward = the gradient kernels, with grad_output folded into their epilogues (the four gradients
-    depend on the logits and a scalar only)."""
+    depend on the logits and a scalar only).
+    normalize=True additionally fuses F.normalize of both inputs (forward) and its backward around the loss."""
 
     @staticmethod
-    def forward(ctx, img, txt, t_prime, bias, engine: SigmoidLossEngine):
+    def forward(ctx, img, txt, t_prime, bias, engine: SigmoidLossEngine, normalize: bool = False):
         need_grad = any(ctx.needs_input_grad[:4])
-        img_b = img.detach().to(torch.bfloat16).contiguous()
-        txt_b = txt.detach().to(torch.bfloat16).contiguous()
+        raw = None
+        if normalize:
+            def prep(x):
+                x = x.detach()
+                if x.dtype not in (torch.float32, torch.bfloat16):
+                    x = x.float()
+                return x.contiguous()
+            img_r, txt_r = prep(img), prep(txt)
+            img_b, inv_i = engine.normalize_fwd(img_r)
+            txt_b, inv_t = engine.normalize_fwd(txt_r)
+            raw = (img_r, txt_r, inv_i, inv_t)
+        else:
+            img_b = img.detach().to(torch.bfloat16).contiguous()
+            txt_b = txt.detach().to(torch.bfloat16).contiguous()
         tp = t_prime.detach().to(device=img.device, dtype=torch.float32).reshape(1)
         b = bias.detach().to(device=img.device, dtype=torch.float32).reshape(1)
         loss = engine.forward(img_b, txt_b, tp, b, need_grad)
         if need_grad:
-            ctx.save_for_backward(img_b, txt_b, tp, b)
+            if raw is not None:
+                ctx.save_for_backward(img_b, txt_b, tp, b, *raw)
+            else:
+                ctx.save_for_backward(img_b, txt_b, tp, b)
+            ctx.normalize = normalize
             ctx.engine = engine
             ctx.gen = engine.saved_generation
             ctx.in_meta = (img.dtype, txt.dtype, t_prime.dtype, bias.dtype, t_prime.shape, bias.shape,
@@ -244,7 +283,8 @@ class _SigmoidLossFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, grad_out):
-        img_b, txt_b, tp, b = ctx.saved_tensors
+        saved = ctx.saved_tensors
+        img_b, txt_b, tp, b = saved[:4]
         eng = ctx.engine
         idt, tdt, pdt, bdt, pshape, bshape, pdev, bdev = ctx.in_meta
         if eng.saved_generation != ctx.gen:
@@ -253,14 +293,21 @@ class _SigmoidLossFn(torch.autograd.Function):
             eng.forward(img_b, txt_b, tp, b, True)
             ctx.gen = eng.saved_generation
         g = grad_out.detach().to(torch.float32).reshape(1).contiguous()
-        # gradients in the dtype autograd would return for these inputs: bf16 straight from the kernel epilogue
-        gdt = torch.bfloat16 if (idt == torch.bfloat16 and tdt == torch.bfloat16) else torch.float32
-        dimg, dtxt, dtp, db = eng.backward(img_b, txt_b, tp, g, gdt)
-        gi = dimg.to(idt) if ctx.needs_input_grad[0] else None
-        gt = dtxt.to(tdt) if ctx.needs_input_grad[1] else None
+        if ctx.normalize:
+            # fp32 gradients w.r.t. the normalised embeddings, then the projection of F.normalize's backward
+            img_r, txt_r, inv_i, inv_t = saved[4:]
+            dimg, dtxt, dtp, db = eng.backward(img_b, txt_b, tp, g, torch.float32)
+            gi = eng.normalize_bwd(img_r, inv_i, dimg).to(idt) if ctx.needs_input_grad[0] else None
+            gt = eng.normalize_bwd(txt_r, inv_t, dtxt).to(tdt) if ctx.needs_input_grad[1] else None
+        else:
+            # gradients in the dtype autograd would return for these inputs: bf16 straight from the kernel epilogue
+            gdt = torch.bfloat16 if (idt == torch.bfloat16 and tdt == torch.bfloat16) else torch.float32
+            dimg, dtxt, dtp, db = eng.backward(img_b, txt_b, tp, g, gdt)
+            gi = dimg.to(idt) if ctx.needs_input_grad[0] else None
+            gt = dtxt.to(tdt) if ctx.needs_input_grad[1] else None
         gp = dtp.reshape(pshape).to(device=pdev, dtype=pdt) if ctx.needs_input_grad[2] else None
         gb = db.reshape(bshape).to(device=bdev, dtype=bdt) if ctx.needs_input_grad[3] else None
-        return gi, gt, gp, gb, None
+        return gi, gt, gp, gb, None, None
 
 
 class _EngineCache:
@@ -305,11 +352,14 @@ class DDPSigmoidLoss(nn.Module):
     Every rank of ``group`` must call ``forward`` the same number of times (collective, like all_gather).
     """
 
-    def __init__(self, gpu_batch_size: int, group=None, cta_group: int = 2, overlap_pull: bool = True) -> None:
+    def __init__(self, gpu_batch_size: int, group=None, cta_group: int = 2, overlap_pull: bool = True,
+                 normalize_inputs: bool = False) -> None:
         super().__init__()
         self.t_prime = nn.Parameter(torch.tensor(math.log(10), dtype=torch.float64))
         self.bias = nn.Parameter(torch.tensor(-10.0))
         self.gpu_batch_size = gpu_batch_size
+        # extension (SURVEY.md §8f-1): take raw encoder outputs and fuse F.normalize (and its backward) around the loss
+        self.normalize_inputs = normalize_inputs
         self._cache = _EngineCache(group, cta_group, overlap_pull)
 
     def engine_for(self, batch: int, dim: int, device: torch.device) -> SigmoidLossEngine:
@@ -318,7 +368,8 @@ class DDPSigmoidLoss(nn.Module):
     def forward(self, image_embeddings: torch.Tensor, text_embeddings: torch.Tensor) -> torch.Tensor:
         _validate(image_embeddings, text_embeddings, self.gpu_batch_size)
         eng = self._cache.get(image_embeddings.shape[0], image_embeddings.shape[1], image_embeddings.device)
-        return _SigmoidLossFn.apply(image_embeddings, text_embeddings, self.t_prime, self.bias, eng)
+        return _SigmoidLossFn.apply(image_embeddings, text_embeddings, self.t_prime, self.bias, eng,
+                                    self.normalize_inputs)
 
 
 SigmoidLoss = DDPSigmoidLoss

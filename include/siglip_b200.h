@@ -90,6 +90,18 @@ int siglip_fwd_bwd(siglip_ctx* ctx, const void* img, const void* txt, const floa
                    float* loss, void* dimg, void* dtxt, float* dt_prime, float* dbias, void* cuda_stream);
 
 /*
+ * L2 normalisation fused around the loss (the step the reference's callers run immediately before it:
+ * F.normalize, test_distributed_sigmoid_loss.py:99-101, README.md:34). [B, D] rows, D % 8 == 0:
+ *   fwd: xhat = bf16(x / max(||x||, 1e-12)) and inv_norm[r] = 1 / max(||x_r||, 1e-12); x is fp32 (in_bf16 = 0) or bf16
+ *   bwd: dx = inv_norm * (dxhat - xhat <xhat, dxhat>) with xhat recomputed in fp32 from x; dxhat fp32 or bf16
+ *        (grad_bf16), dx in x's dtype — autograd's backward of F.normalize composed with the loss gradients.
+ */
+int siglip_normalize_fwd(siglip_ctx* ctx, const void* x, int in_bf16, void* xhat_bf16, float* inv_norm,
+                         void* cuda_stream);
+int siglip_normalize_bwd(siglip_ctx* ctx, const void* x, int in_bf16, const float* inv_norm, const void* dxhat,
+                         int grad_bf16, void* dx, void* cuda_stream);
+
+/*
  * dst = src * (*g) elementwise over `nbytes` of fp32 (is_bf16 = 0) or bf16 (is_bf16 = 1) data: the whole
  * `backward()` of the module — the fused step already produced the gradients for an upstream gradient of 1
  * (replaces the autograd graph replay of SURVEY.md §3.2). `g` is a device scalar (grad_output).

@@ -34,13 +34,14 @@ def _max_rel(a, b):
     return float((a - b).abs().max() / (b.abs().max() + 1e-300))
 
 
-def _check(name, got, ref, tol=TOL):
+def _check(name, got, ref, tol=TOL, max_tol=None):
     if np.ndim(ref) == 0 and not torch.is_tensor(ref):
         err = abs(float(got) - float(ref)) / (abs(float(ref)) + 1e-30)
         assert err <= tol, f"{name}: {float(got)} vs {float(ref)} (rel {err:.3e})"
     else:
         ef, em = _rel_f(got, ref), _max_rel(got, ref)
-        assert ef <= tol and em <= tol, f"{name}: rel-Frobenius {ef:.3e}, max-abs/max {em:.3e}"
+        mt = tol if max_tol is None else max_tol
+        assert ef <= tol and em <= mt, f"{name}: rel-Frobenius {ef:.3e}, max-abs/max {em:.3e}"
 
 
 def _engine(B, D, cg=2, **kw):
@@ -397,6 +398,45 @@ def test_split_forward_backward_and_generation_guard():
     _check("graph 1 dimg", a1.grad.float(), r1, tol=4e-3)
     _check("graph 2 dimg", a2.grad.float(), r2, tol=4e-3)
     e1.close()
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_fused_l2_normalisation(dtype):
+    """normalize_inputs=True: raw encoder outputs in, F.normalize + loss + both backwards fused. Oracle: torch autograd
+    of F.normalize -> (straight-through bf16 rounding, the input contract of the loss) -> fp32 loss."""
+    from distributed_sigmoid_loss_b200 import DDPSigmoidLoss
+
+    B, D = 1024, 384
+    g = torch.Generator().manual_seed(3)
+    x = (torch.randn(B, D, generator=g) * 3.0 + 0.2).to(dtype).to(_dev())
+    y = (torch.randn(B, D, generator=g) * 0.5).to(dtype).to(_dev())
+    mod = DDPSigmoidLoss(B, normalize_inputs=True).to(_dev())
+    a, b = x.clone().requires_grad_(True), y.clone().requires_grad_(True)
+    loss = mod(a, b)
+    loss.backward()
+
+    def ref_side(v):
+        v32 = v.detach().float().requires_grad_(True)
+        n = torch.nn.functional.normalize(v32)
+        n = n + (n.to(torch.bfloat16).float() - n).detach()      # rounding to bf16, gradient passes straight through
+        return v32, n
+
+    a32, an = ref_side(x)
+    b32, bn = ref_side(y)
+    t = torch.tensor(float(mod.t_prime), device=_dev(), requires_grad=True)
+    bb = torch.tensor(float(mod.bias), device=_dev(), requires_grad=True)
+    z = an @ bn.T * t.exp() + bb
+    ref = (-torch.nn.functional.logsigmoid((2 * torch.eye(B, device=_dev()) - 1) * z)).sum() / B
+    ref.backward()
+    torch.cuda.synchronize()
+    tol = 1e-3 if dtype == torch.float32 else 4e-3      # bf16 leaves: the returned gradient is rounded to bf16
+    _check("loss", loss.detach(), float(ref))
+    # the projection (I - xhat xhat^T) cancels the radial part of the loss gradient: single elements of rows with a
+    # small norm amplify the 1e-4 error of dxhat; the matrix-level error stays ~3e-5 (observed)
+    _check("d raw img", a.grad.float(), a32.grad, tol=tol, max_tol=5e-3)
+    _check("d raw txt", b.grad.float(), b32.grad, tol=tol, max_tol=5e-3)
+    _check("dt_prime", mod.t_prime.grad, float(t.grad))
+    _check("dbias", mod.bias.grad, float(bb.grad))
 
 
 def test_kernel_launch_accounting():
