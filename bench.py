@@ -99,6 +99,20 @@ class ClockSampler:
                 "reasons": reasons, "samples": len(sel)}
 
 
+def _bind_to_gpu_numa_node(gpu_index: int):
+    """Pin this process to the CPUs NVML reports as local to the GPU, so that pinned host memory is allocated on the
+    GPU's NUMA node (host->device copies of the e2e path cross no socket link). Best effort."""
+    try:
+        import pynvml
+
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(gpu_index)
+        pynvml.nvmlDeviceSetCpuAffinity(h)
+        return sorted(os.sched_getaffinity(0))[:1] + [len(os.sched_getaffinity(0))]
+    except Exception:
+        return None
+
+
 def synth(rank: int, B: int, D: int):
     import torch
 
@@ -209,6 +223,7 @@ def run_ours(args):
         raise SystemExit("bench.py needs a B200: the product path has no CPU fallback (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    numa = _bind_to_gpu_numa_node(local_rank)   # pinned host buffers next to the GPU's PCIe root (matters for e2e)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     B, D, W = args.batch, args.dim, world
@@ -310,7 +325,8 @@ def run_ours(args):
             "tflops_per_gpu": 6.0 * B * (W * B) * D / (ms_step * 1e-3) / 1e12,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 2 * B * D * 2, "d2h_bytes_per_step": 12,
                     "ms_per_step": e2e_s * 1e3,
-                    "api": "siglip_fwd_bwd_host (pinned host bf16 in, loss/dt'/dbias out, grads stay on device)"},
+                    "api": "siglip_fwd_bwd_host (pinned host bf16 in, loss/dt'/dbias out, grads stay on device)",
+                    "cpu_affinity": numa},
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": {"bound": "tensor", "kernel": "siglip_gemm_kernel<cg,1> (dimg + dtxt contractions)",
