@@ -99,6 +99,9 @@ class ClockSampler:
                 "reasons": reasons, "samples": len(sel)}
 
 
+_ORIGINAL_AFFINITY = None
+
+
 def _bind_to_gpu_numa_node(gpu_index: int):
     """Pin this process to the CPUs NVML reports as local to the GPU, so that pinned host memory is allocated on the
     GPU's NUMA node (host->device copies of the e2e path cross no socket link). Best effort."""
@@ -107,6 +110,8 @@ def _bind_to_gpu_numa_node(gpu_index: int):
 
         pynvml.nvmlInit()
         h = pynvml.nvmlDeviceGetHandleByIndex(gpu_index)
+        global _ORIGINAL_AFFINITY
+        _ORIGINAL_AFFINITY = os.sched_getaffinity(0)
         pynvml.nvmlDeviceSetCpuAffinity(h)
         return sorted(os.sched_getaffinity(0))[:1] + [len(os.sched_getaffinity(0))]
     except Exception:
@@ -337,6 +342,8 @@ def run_ours(args):
                                          "avg_launch_ms": loss_avg_ms, "launches_timed": loss_n}},
         }
         if W == 1 and not args.no_cpu_baseline:
+            if _ORIGINAL_AFFINITY is not None:
+                os.sched_setaffinity(0, _ORIGINAL_AFFINITY)   # the CPU baseline may use every host core
             v, sec, threads = cpu_reference_rate(B, D, 1, args.cpu_sample_rows, 3, 1)
             line["cpu_baseline"] = {
                 "value": v, "unit": UNIT, "cores": threads, "kind": "port",
