@@ -124,6 +124,16 @@ __device__ __forceinline__ void wait_peer_flag(const volatile unsigned int* flag
   asm volatile("bar.sync 2, 64;" ::: "memory");
 }
 
+// 16-byte load of peer (NVLink-mapped) or streaming data: no L1 allocation, data is touched once
+__device__ __forceinline__ uint4 ld_peer_16(const uint4* p) {
+  uint4 v;
+  asm volatile("ld.global.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+               : "l"(p)
+               : "memory");
+  return v;
+}
+
 struct TileCoord {
   int prob;
   int m_blk;
@@ -665,18 +675,15 @@ siglip_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_consta
       const unsigned long long n16 = p.pull_bytes >> 4;
       const unsigned long long nthreads = static_cast<unsigned long long>(gridDim.x) * 64ull;
       unsigned long long i = static_cast<unsigned long long>(blockIdx.x) * 64ull + (threadIdx.x - kAllocWarp * 32);
-      // 4 independent 16-byte loads in flight per thread to cover the ~2 us NVLink round trip
-      for (; i + 3ull * nthreads < n16; i += 4ull * nthreads) {
-        uint4 a = p.pull_src[i];
-        uint4 b = p.pull_src[i + nthreads];
-        uint4 c = p.pull_src[i + 2ull * nthreads];
-        uint4 d = p.pull_src[i + 3ull * nthreads];
-        p.pull_dst[i] = a;
-        p.pull_dst[i + nthreads] = b;
-        p.pull_dst[i + 2ull * nthreads] = c;
-        p.pull_dst[i + 3ull * nthreads] = d;
+      // 8 independent 16-byte peer loads in flight per thread (~1.2 MB per GPU) to cover the NVLink round trip
+      for (; i + 7ull * nthreads < n16; i += 8ull * nthreads) {
+        uint4 v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) v[u] = ld_peer_16(p.pull_src + i + u * nthreads);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) p.pull_dst[i + u * nthreads] = v[u];
       }
-      for (; i < n16; i += nthreads) p.pull_dst[i] = p.pull_src[i];
+      for (; i < n16; i += nthreads) p.pull_dst[i] = ld_peer_16(p.pull_src + i);
     }
     // bf16 -> scaled fp16 copies of the embeddings for the gradient kernel (its sigma operand is fp16, and an
     // MMA cannot mix fp16 with bf16): done here, off the critical path, while the tiles of this chunk compute.
@@ -709,22 +716,29 @@ siglip_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_consta
       if (p.acc_wait_flag != nullptr) wait_peer_flag(p.acc_wait_flag, p.acc_wait_value, p.dbg, 7);
       const unsigned long long nthreads = static_cast<unsigned long long>(gridDim.x) * 64ull;
       unsigned long long i = static_cast<unsigned long long>(blockIdx.x) * 64ull + (threadIdx.x - kAllocWarp * 32);
-      for (; i + 3ull * nthreads < p.acc_n4; i += 4ull * nthreads) {
-        float4 r0 = p.acc_remote[i], r1 = p.acc_remote[i + nthreads];
-        float4 r2 = p.acc_remote[i + 2ull * nthreads], r3 = p.acc_remote[i + 3ull * nthreads];
-        const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
-        const bool has_in = p.acc_in != nullptr;   // first contribution of a step: plain copy
-        const float4 a0 = has_in ? p.acc_in[i] : z4, a1 = has_in ? p.acc_in[i + nthreads] : z4;
-        const float4 a2 = has_in ? p.acc_in[i + 2ull * nthreads] : z4, a3 = has_in ? p.acc_in[i + 3ull * nthreads] : z4;
-        p.acc_out[i] = make_float4(a0.x + r0.x, a0.y + r0.y, a0.z + r0.z, a0.w + r0.w);
-        p.acc_out[i + nthreads] = make_float4(a1.x + r1.x, a1.y + r1.y, a1.z + r1.z, a1.w + r1.w);
-        p.acc_out[i + 2ull * nthreads] = make_float4(a2.x + r2.x, a2.y + r2.y, a2.z + r2.z, a2.w + r2.w);
-        p.acc_out[i + 3ull * nthreads] = make_float4(a3.x + r3.x, a3.y + r3.y, a3.z + r3.z, a3.w + r3.w);
+      const bool has_in = p.acc_in != nullptr;   // first contribution of a backward pass: plain copy
+      for (; i + 7ull * nthreads < p.acc_n4; i += 8ull * nthreads) {
+        uint4 rv[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) rv[u] = ld_peer_16(reinterpret_cast<const uint4*>(p.acc_remote) + i + u * nthreads);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          float4 a = has_in ? p.acc_in[i + u * nthreads] : make_float4(0.f, 0.f, 0.f, 0.f);
+          a.x += __uint_as_float(rv[u].x);
+          a.y += __uint_as_float(rv[u].y);
+          a.z += __uint_as_float(rv[u].z);
+          a.w += __uint_as_float(rv[u].w);
+          p.acc_out[i + u * nthreads] = a;
+        }
       }
       for (; i < p.acc_n4; i += nthreads) {
-        const float4 rr = p.acc_remote[i];
-        const float4 aa = (p.acc_in != nullptr) ? p.acc_in[i] : make_float4(0.f, 0.f, 0.f, 0.f);
-        p.acc_out[i] = make_float4(aa.x + rr.x, aa.y + rr.y, aa.z + rr.z, aa.w + rr.w);
+        const uint4 rr = ld_peer_16(reinterpret_cast<const uint4*>(p.acc_remote) + i);
+        float4 a = has_in ? p.acc_in[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+        a.x += __uint_as_float(rr.x);
+        a.y += __uint_as_float(rr.y);
+        a.z += __uint_as_float(rr.z);
+        a.w += __uint_as_float(rr.w);
+        p.acc_out[i] = a;
       }
     }
   }
