@@ -59,6 +59,8 @@ SIGLIP_OPT_STAGES_GRAD = 5
 SIGLIP_OPT_MCAST = 6
 SIGLIP_OPT_GRAD_BF16 = 7
 SIGLIP_OPT_OVERLAP_REDUCE = 8
+SIGLIP_OPT_EPI_SLEEP_GRAD_NS = 9
+SIGLIP_OPT_EPI_SLEEP_LOSS_NS = 10
 
 _lib: Optional[ctypes.CDLL] = None
 

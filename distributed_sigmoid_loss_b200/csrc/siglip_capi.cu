@@ -134,6 +134,8 @@ struct siglip_ctx {
   int stages_loss = 0, stages_grad = 0;  // 0 = kernel default
   int mcast = 2;                         // B-tile multicast cluster size for cta_group 1 (1 = off)
   int grad_bf16 = 0;                     // dimg / dtxt outputs are bf16 instead of fp32
+  int epi_sleep_grad_ns = 0;             // back-off of the gradient kernel's epilogue warps while a K loop runs
+  int epi_sleep_loss_ns = 0;
   // workspaces
   __nv_bfloat16* txt_all = nullptr;      // [world][B, D] bf16; slot `rank` is what the peers pull (world > 1)
   __nv_bfloat16* G[kMaxWorld] = {};      // per step k: [Bp, Bp] sigma operand (fp16 bits x kGScale), diagonal zeroed
@@ -256,6 +258,7 @@ int run_loss_chunk(siglip_ctx* c, int k, const void* img, const __nv_bfloat16* t
   p.pull_bytes = pull.bytes;
   p.pull_wait_flag = pull.flag;
   p.pull_wait_value = pull.value;
+  p.epi_sleep_ns = static_cast<unsigned int>(c->epi_sleep_loss_ns);
   if (save && getenv("SIGLIP_DEBUG_NO_GSTORE")) p.store_g = 0;  // timing experiments only (wrong gradients)
   if (save && !getenv("SIGLIP_DEBUG_NO_CVT")) {
     const size_t chunk_elems = static_cast<size_t>(c->B) * c->D;
@@ -336,6 +339,7 @@ int run_grad_chunk(siglip_ctx* c, int k, const void* img, const __nv_bfloat16* t
     p.acc_wait_flag = fold.flag;
     p.acc_wait_value = fold.value;
   }
+  p.epi_sleep_ns = static_cast<unsigned int>(c->epi_sleep_grad_ns);
   p.t_prime = t_prime;
   p.grad_out = grad_out;
   p.inv_b = 1.0f / static_cast<float>(c->B);
@@ -607,6 +611,12 @@ int siglip_ctx_set_option(siglip_ctx* c, int option, int value) {
     case SIGLIP_OPT_MCAST:
       if (value != 1 && value != 2) return fail(SIGLIP_ERR_INVALID, "mcast must be 1 or 2");
       c->mcast = value;
+      return 0;
+    case SIGLIP_OPT_EPI_SLEEP_GRAD_NS:
+      c->epi_sleep_grad_ns = value < 0 ? 0 : value;
+      return 0;
+    case SIGLIP_OPT_EPI_SLEEP_LOSS_NS:
+      c->epi_sleep_loss_ns = value < 0 ? 0 : value;
       return 0;
     case SIGLIP_OPT_STAGES_LOSS:
       c->stages_loss = value;

@@ -41,6 +41,8 @@ enum {
   SIGLIP_OPT_STAGES_GRAD = 5,  /* ... of the gradient kernel */
   SIGLIP_OPT_MCAST = 6,        /* cta_group 1 only: 2 (default) = clusters of two CTAs share the B tile by TMA multicast */
   SIGLIP_OPT_OVERLAP_REDUCE = 8, /* 1 (default): fold the peers' dtxt contributions in step by step inside the gradient kernels; 0: one reduction at the end */
+  SIGLIP_OPT_EPI_SLEEP_GRAD_NS = 9, /* nanosleep back-off of the epilogue warps while they wait for an accumulator (gradient kernel) */
+  SIGLIP_OPT_EPI_SLEEP_LOSS_NS = 10, /* ... (loss kernel) */
   SIGLIP_OPT_GRAD_BF16 = 7     /* 1: siglip_fwd_bwd writes dimg / dtxt as bf16 [B, D] (the dtype autograd returns for bf16 inputs); default 0 = fp32 */
 };
 
