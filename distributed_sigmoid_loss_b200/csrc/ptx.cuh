@@ -167,6 +167,18 @@ __device__ __forceinline__ void tma_load_2d_mcast(const CUtensorMap* m, uint32_t
       : "memory");
 }
 
+// cta_group::2 flavour of the multicast load (2x2 clusters: two MMA pairs share an operand tile). `bar` is THIS CTA's
+// barrier offset with the pair bit cleared (bit 24 of a shared::cluster address selects the CTA within an MMA pair):
+// in every destination CTA the complete_tx lands on the barrier of that destination's pair LEADER.
+__device__ __forceinline__ void tma_load_2d_mcast_2sm(const CUtensorMap* m, uint32_t bar, uint32_t dst, int c0, int c1,
+                                                      uint16_t cta_mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster"
+      " [%0], [%1, {%4, %5}], [%2], %3;" ::"r"(dst),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(bar & 0xFEFFFFFFu), "h"(cta_mask), "r"(c0), "r"(c1)
+      : "memory");
+}
+
 // ---------------------------------------------------------------------------------------------
 // tcgen05: TMEM allocation, MMA, commit, TMEM loads
 // ---------------------------------------------------------------------------------------------
@@ -236,6 +248,15 @@ __device__ __forceinline__ void umma_commit(uint32_t bar) {
 __device__ __forceinline__ void umma_commit_mcast(uint32_t bar, uint16_t cta_mask) {
   asm volatile(
       "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+      "h"(cta_mask)
+      : "memory");
+}
+
+// cta_group::2 commit with an explicit cluster CTA mask (2x2 clusters: a stage is released in all four CTAs, an
+// accumulator is published to the two CTAs of one pair)
+__device__ __forceinline__ void umma_commit_2sm_mask(uint32_t bar, uint16_t cta_mask) {
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
       "h"(cta_mask)
       : "memory");
 }

@@ -132,7 +132,7 @@ struct siglip_ctx {
   int overlap_reduce = 1;                // fold the peers' dtxt contributions inside the gradient kernels
   int kernel_timing = 0;
   int stages_loss = 0, stages_grad = 0;  // 0 = kernel default
-  int mcast = 2;                         // B-tile multicast cluster size for cta_group 1 (1 = off)
+  int mcast = 1;                         // 2: vertically adjacent tiles share the B tile by TMA multicast
   int grad_bf16 = 0;                     // dimg / dtxt outputs are bf16 instead of fp32
   int epi_sleep_grad_ns = 0;             // back-off of the gradient kernel's epilogue warps while a K loop runs
   int epi_sleep_loss_ns = 0;
@@ -227,7 +227,7 @@ int run_loss_chunk(siglip_ctx* c, int k, const void* img, const __nv_bfloat16* t
   __nv_bfloat16* G = c->G[save ? k : 0];
   CUtensorMap tmA, tmB, tmG;
   if ((rc = encode_operand(&tmA, img, c->B, c->D, c->D, 0, 128))) return rc;
-  const int mc = (cg == 1) ? c->mcast : 1;
+  const int mc = c->mcast;
   if ((rc = encode_operand(&tmB, txt_c, c->B, c->D, c->D, 0, 256 / (cg * mc)))) return rc;
   // store map of the sigma operand: [B, B] inside the padded [Bp, Bp] buffer, one 32x32 slab per TMA store
   if ((rc = encode_bf16_2d(&tmG, G, (uint64_t)c->B, (uint64_t)c->B, (uint64_t)c->Bp, 32, 32,
@@ -345,7 +345,7 @@ int run_grad_chunk(siglip_ctx* c, int k, const void* img, const __nv_bfloat16* t
   p.inv_b = 1.0f / static_cast<float>(c->B);
   p.dbg = c->dbg_dev;
   if ((rc = timing_mark(c, c->ev_grad, c->ev_grad_used, st))) return rc;
-  CKI(siglip::launch_gemm(cg, siglip::kModeOut, c->stages_grad, (cg == 1) ? c->mcast : 1, &tmA0, &tmB0, &tmA1, &tmB1,
+  CKI(siglip::launch_gemm(cg, siglip::kModeOut, c->stages_grad, c->mcast, &tmA0, &tmB0, &tmA1, &tmB1,
                           &tmA0, p, c->num_sms, st));
   if ((rc = timing_mark(c, c->ev_grad, c->ev_grad_used, st))) return rc;
   c->launches++;
@@ -892,7 +892,7 @@ int siglip_debug_gemm_timed(int device, int cta_group, int M, int N, int K, cons
   int rc;
   if ((rc = encode_operand(&tmA, A, M, K, lda, a_mn, 128))) return rc;
   const char* env_mc = getenv("SIGLIP_DEBUG_MCAST");
-  const int mcast = (cta_group == 1 && env_mc) ? atoi(env_mc) : 1;
+  const int mcast = env_mc ? atoi(env_mc) : 1;
   if ((rc = encode_operand(&tmB, Bm, N, K, ldb, b_mn, 256 / (cta_group * mcast)))) return rc;
   float* zero = nullptr;  // t' = 0 -> scale exp(0) * 1 = 1
   CK(cudaMalloc(reinterpret_cast<void**>(&zero), sizeof(float)));

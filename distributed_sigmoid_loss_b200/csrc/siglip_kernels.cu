@@ -17,6 +17,9 @@
 // instantiated; the host picks one.
 #include "siglip_kernels.cuh"
 
+#include <stdio.h>
+#include <stdlib.h>
+
 namespace siglip {
 
 namespace {
@@ -346,12 +349,15 @@ siglip_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_consta
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  static_assert(kMC == 1 || kCG == 1, "operand multicast is implemented for cta_group::1 clusters");
+  static_assert(kMC == 1 || kMC == 2, "operand multicast across 1 or 2 tiles");
+  // Cluster layout: kCG consecutive CTAs form one MMA pair; kMC pairs (or single CTAs) on vertically adjacent tiles
+  // share the B operand tile by TMA multicast. cg=2, mc=2 is the 2x2 cluster cuBLAS' nvjet kernels use.
   constexpr int kClusterSize = kCG * kMC;
   const uint32_t crank = (kClusterSize > 1) ? cluster_ctarank() : 0u;
-  const uint32_t cta_rank = (kCG == 2) ? crank : 0u;      // rank inside the MMA pair
-  const int mc_rank = (kMC > 1) ? static_cast<int>(crank) : 0;  // which of the cluster's tiles this CTA computes
-  constexpr uint16_t kMcMask = static_cast<uint16_t>((1u << kMC) - 1u);
+  const uint32_t cta_rank = (kCG == 2) ? (crank & 1u) : 0u;                 // rank inside the MMA pair
+  const int mc_rank = (kMC > 1) ? static_cast<int>(crank / kCG) : 0;         // which of the cluster's tiles
+  const uint32_t leader_rank = crank - cta_rank;                             // cluster rank of this pair's leader
+  constexpr uint16_t kMcMask = static_cast<uint16_t>((1u << kClusterSize) - 1u);  // every CTA of the cluster
   const int cluster_id = blockIdx.x / kClusterSize;
   const int num_clusters = gridDim.x / kClusterSize;
   const int total_tiles = cluster_tiles<kMC>(p.prob[0]) + (p.nprob > 1 ? cluster_tiles<kMC>(p.prob[1]) : 0);
@@ -396,7 +402,6 @@ siglip_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_consta
       int stage = 0;
       uint32_t phase = 0;
       long long w_empty = 0;
-      const uint32_t full_owner_rank = 0;  // the pair's leader CTA owns the "full" barriers
       for (int t = cluster_id; t < total_tiles; t += num_clusters) {
         const TileCoord tc = decode_tile<kMC>(p, t, mc_rank);
         const Problem& pr = p.prob[tc.prob];
@@ -413,7 +418,8 @@ siglip_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_consta
             const uint32_t sB = sA + C::kABytes;
             uint32_t fb = full_bar(stage);
             if (cta_rank == 0) mbar_arrive_expect_tx(fb, C::kStageBytes * kCG);
-            if constexpr (kCG == 2) fb = mapa_shared(fb, full_owner_rank);
+            const uint32_t fb_local = fb;
+            if constexpr (kCG == 2) fb = mapa_shared(fb, leader_rank);   // the pair's leader owns the full barriers
             const int k_idx = kb * kBlockK;
             if (!a_mn) {
               tma_load_2d<kCG>(tmA, fb, sA, k_idx, m_idx);  // box {64 k, 128 rows}
@@ -430,7 +436,7 @@ siglip_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_consta
                 for (int h = 0; h < C::kBRows / 64; ++h)
                   tma_load_2d<kCG>(tmB, fb, sB + h * 8192, n_idx + 64 * h, k_idx);
               }
-            } else {
+            } else if constexpr (kCG == 1) {
               // this CTA fetches 1/kMC of the common B tile and multicasts it to every CTA of the cluster
               constexpr int kPart = C::kBRows / kMC;  // rows of B per CTA
               if (!b_mn) {
@@ -442,6 +448,18 @@ siglip_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_consta
                   const int hh = mc_rank * (kPart / 64) + h;
                   tma_load_2d_mcast(tmB, fb, sB + hh * 8192, n_idx + 64 * hh, k_idx, kMcMask);
                 }
+              }
+            } else {
+              // 2x2 cluster: the CTAs with the same rank-in-pair of both pairs hold the same 128 B rows; each of them
+              // fetches 64 of those rows and multicasts them to both. The bytes are counted on each pair leader's
+              // full barrier (pair bit cleared in the barrier address).
+              constexpr int kPart = C::kBRows / kMC;  // 64 rows
+              const uint16_t mask = static_cast<uint16_t>(0x5u << cta_rank);   // CTAs {cta_rank, cta_rank + 2}
+              if (!b_mn) {
+                tma_load_2d_mcast_2sm(tmB, fb_local, sB + mc_rank * (kPart * kBlockK * 2), k_idx,
+                                      n_idx + mc_rank * kPart, mask);          // box {64 k, 64 rows}
+              } else {
+                tma_load_2d_mcast_2sm(tmB, fb_local, sB + mc_rank * 8192, n_idx + 64 * mc_rank, k_idx, mask);
               }
             }
           }
@@ -495,12 +513,20 @@ siglip_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_consta
                              bdesc + static_cast<uint64_t>(k * b_adv), idesc, static_cast<uint32_t>((kb | k) != 0));
             }
             c1 = prof ? clock_cycles() : 0;
-            if constexpr (kMC > 1) {
+            if constexpr (kMC > 1 && kCG == 1) {
               umma_commit_mcast(empty_bar(stage), kMcMask);  // stage is free in every CTA that writes into it
+            } else if constexpr (kMC > 1) {
+              umma_commit_2sm_mask(empty_bar(stage), kMcMask);   // all four CTAs of the 2x2 cluster
             } else {
               umma_commit<kCG>(empty_bar(stage));  // frees the smem stage (both CTAs) when the MMAs retire
             }
-            if (kb == num_kb - 1) umma_commit<kCG>(tmem_full_bar(as));  // accumulator ready (both CTAs)
+            if (kb == num_kb - 1) {                // accumulator ready for the epilogue warps of this pair
+              if constexpr (kMC > 1 && kCG == 2) {
+                umma_commit_2sm_mask(tmem_full_bar(as), static_cast<uint16_t>(0x3u << leader_rank));
+              } else {
+                umma_commit<kCG>(tmem_full_bar(as));
+              }
+            }
             if (prof) {
               const long long c2 = clock_cycles();
               w_issue += c1 - c0;
@@ -545,7 +571,7 @@ siglip_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_consta
     uint32_t empty_remote[kAccStages];
 #pragma unroll
     for (int a = 0; a < kAccStages; ++a) {
-      empty_remote[a] = (kCG == 2) ? mapa_shared(tmem_empty_bar(a), 0) : tmem_empty_bar(a);
+      empty_remote[a] = (kCG == 2) ? mapa_shared(tmem_empty_bar(a), leader_rank) : tmem_empty_bar(a);
     }
     for (int t = cluster_id; t < total_tiles; t += num_clusters) {
       const TileCoord tc = decode_tile<kMC>(p, t, mc_rank);
@@ -979,11 +1005,7 @@ int launch_impl(const CUtensorMap* tmA0, const CUtensorMap* tmB0, const CUtensor
   if (e != cudaSuccess) return static_cast<int>(e);
   int total_tiles = ((p.prob[0].tiles_m + kMC - 1) / kMC) * p.prob[0].tiles_n;
   if (p.nprob > 1) total_tiles += ((p.prob[1].tiles_m + kMC - 1) / kMC) * p.prob[1].tiles_n;
-  int grid = (num_sms / kClusterSize) * kClusterSize;
-  if (grid > total_tiles * kClusterSize) grid = total_tiles * kClusterSize;
-  if (grid < kClusterSize) grid = kClusterSize;
   cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3(grid);
   cfg.blockDim = dim3(kNumThreads);
   cfg.dynamicSmemBytes = C::kSmemBytes;
   cfg.stream = stream;
@@ -994,6 +1016,23 @@ int launch_impl(const CUtensorMap* tmA0, const CUtensorMap* tmB0, const CUtensor
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
+  // A persistent kernel must have every cluster co-resident: clusters of 4 do not tile every GPC, so ask the runtime
+  // how many fit (once per instantiation) instead of assuming num_sms / cluster size.
+  static int max_clusters = -1;
+  if (max_clusters < 0) {
+    cfg.gridDim = dim3((num_sms / kClusterSize) * kClusterSize);
+    int n = 0;
+    if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) != cudaSuccess || n <= 0) {
+      cudaGetLastError();
+      n = num_sms / kClusterSize;
+    }
+    max_clusters = n;
+    if (getenv("SIGLIP_DEBUG_WAITSTATS")) printf("[launch] cluster size %d: %d co-resident clusters\n", kClusterSize, n);
+  }
+  int clusters = max_clusters < num_sms / kClusterSize ? max_clusters : num_sms / kClusterSize;
+  if (clusters > total_tiles) clusters = total_tiles;
+  if (clusters < 1) clusters = 1;
+  cfg.gridDim = dim3(clusters * kClusterSize);
   e = cudaLaunchKernelEx(&cfg, kern, *tmA0, *tmB0, *tmA1, *tmB1, *tmG, p);
   return static_cast<int>(e);
 }
@@ -1046,6 +1085,18 @@ int launch_gemm(int cta_group, int mode, int stages, int mcast, const CUtensorMa
                 const CUtensorMap* tmA1, const CUtensorMap* tmB1, const CUtensorMap* tmG, const KernelParams& p,
                 int num_sms, cudaStream_t stream) {
   if (stages <= 0) stages = default_stages(cta_group, mode);
+  if (cta_group == 2 && mcast == 2) {  // 2x2 clusters: two MMA pairs share the B tile by TMA multicast
+    if (mode == kModeLoss) {
+      switch (stages) {
+        case 4: SIGLIP_LAUNCH(2, kModeLoss, 4, 2);
+        default: SIGLIP_LAUNCH(2, kModeLoss, 6, 2);
+      }
+    }
+    switch (stages) {
+      case 4: SIGLIP_LAUNCH(2, kModeOut, 4, 2);
+      default: SIGLIP_LAUNCH(2, kModeOut, 7, 2);
+    }
+  }
   if (cta_group == 2) {  // 2-CTA MMA pairs, no operand multicast
     if (mode == kModeLoss) {
       switch (stages) {

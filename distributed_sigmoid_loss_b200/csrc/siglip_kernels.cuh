@@ -83,8 +83,9 @@ int query_max_active_clusters(int cta_group);  // co-resident clusters of the ou
 // Launch the warp-specialised persistent kernel. `stages` <= 0 selects the default pipeline depth.
 // tmG: store map of the sigma operand (loss mode; bf16 [B, B], box {32, 32}, 64B swizzle) — any valid map in out mode.
 // Returns cudaError_t as int.
-// mcast: 1 = every CTA loads its own operands; 2 (cta_group 1 only) = clusters of two CTAs on vertically adjacent
-// tiles share the B tile through TMA multicast (the K-major B map must then have box rows 128).
+// mcast: 1 = every CTA (pair) loads its own operands; 2 = clusters of two CTAs (cta_group 1) or two MMA pairs
+// (cta_group 2: a 2x2 cluster) on vertically adjacent tiles share the B tile through TMA multicast; the K-major B map
+// must then have box rows 256 / (cta_group * mcast).
 int launch_gemm(int cta_group, int mode, int stages, int mcast, const CUtensorMap* tmA0, const CUtensorMap* tmB0,
                 const CUtensorMap* tmA1, const CUtensorMap* tmB1, const CUtensorMap* tmG, const KernelParams& p,
                 int num_sms, cudaStream_t stream);

@@ -39,7 +39,7 @@ enum {
   SIGLIP_OPT_KERNEL_TIMING = 3, /* 1: bracket every loss / gradient kernel launch with CUDA events on the caller's stream */
   SIGLIP_OPT_STAGES_LOSS = 4,  /* TMA->MMA pipeline depth of the loss kernel (0 = default) */
   SIGLIP_OPT_STAGES_GRAD = 5,  /* ... of the gradient kernel */
-  SIGLIP_OPT_MCAST = 6,        /* cta_group 1 only: 2 (default) = clusters of two CTAs share the B tile by TMA multicast */
+  SIGLIP_OPT_MCAST = 6,        /* 2: vertically adjacent tiles share the B tile by TMA multicast (cta_group 2: 2x2 clusters); default 1 */
   SIGLIP_OPT_OVERLAP_REDUCE = 8, /* 1 (default): fold the peers' dtxt contributions in step by step inside the gradient kernels; 0: one reduction at the end */
   SIGLIP_OPT_EPI_SLEEP_GRAD_NS = 9, /* nanosleep back-off of the epilogue warps while they wait for an accumulator (gradient kernel) */
   SIGLIP_OPT_EPI_SLEEP_LOSS_NS = 10, /* ... (loss kernel) */

@@ -31,7 +31,7 @@ def _gemm_case(cg: int, amn: int, bmn: int) -> int:
     shapes = [(256, 256, 64), (256, 256, 128), (256, 256, 512), (512, 768, 1024), (300, 264, 200), (1024, 1024, 4096),
               (128, 256, 64), (2000, 520, 328)]
     bad = 0
-    for mc in ((1, 2) if cg == 1 else (1,)):
+    for mc in (1, 2):
       os.environ["SIGLIP_DEBUG_MCAST"] = str(mc)
       for (M, N, K) in shapes:
           A = torch.randn(M, K, device=dev).to(torch.bfloat16)
