@@ -150,6 +150,16 @@ __device__ __forceinline__ int cluster_tiles(const Problem& pr) {
   return ((pr.tiles_m + kMC - 1) / kMC) * pr.tiles_n;
 }
 
+// Columns the MMA of column tile n_blk computes: 256, or 128 for a short last tile of the out kernel.
+template <int kMode, int kMC>
+__device__ __forceinline__ int tile_cols(const Problem& pr, int n_blk) {
+  if constexpr (kMode == kModeOut && kMC == 1) {
+    return (pr.b_mn && pr.N - n_blk * kTileN <= kTileN / 2) ? kTileN / 2 : kTileN;
+  } else {
+    return kTileN;
+  }
+}
+
 template <int kMC>
 __device__ __forceinline__ TileCoord decode_tile(const KernelParams& p, int t, int mc_rank) {
   TileCoord c;
@@ -408,7 +418,12 @@ siglip_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_consta
         const CUtensorMap* tmA = tc.prob ? &tmA1 : &tmA0;
         const CUtensorMap* tmB = tc.prob ? &tmB1 : &tmB0;
         const int m_idx = tc.m_blk * C::kTileM + static_cast<int>(cta_rank) * kBlockM;
-        const int n_idx = tc.n_blk * kTileN + static_cast<int>(cta_rank) * C::kBRows;
+        // a last column tile with <= 128 columns left runs as a 128-wide MMA (out mode, N-major B, no multicast):
+        // D = 1152 is 4.5 tiles of 256 — without this 10 % of the gradient MMA work would be padding
+        const int n_cur = tile_cols<kMode, kMC>(pr, tc.n_blk);
+        const int b_rows = n_cur / kCG;                               // B rows this CTA holds for the tile
+        const int n_idx = tc.n_blk * kTileN + static_cast<int>(cta_rank) * b_rows;
+        const uint32_t stage_tx = static_cast<uint32_t>(C::kABytes + b_rows * kBlockK * 2) * kCG;
         const int num_kb = (pr.K + kBlockK - 1) / kBlockK;
         const int a_mn = pr.a_mn, b_mn = pr.b_mn;
         for (int kb = 0; kb < num_kb; ++kb) {
@@ -417,7 +432,7 @@ siglip_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_consta
             const uint32_t sA = smem_base + stage * C::kStageBytes;
             const uint32_t sB = sA + C::kABytes;
             uint32_t fb = full_bar(stage);
-            if (cta_rank == 0) mbar_arrive_expect_tx(fb, C::kStageBytes * kCG);
+            if (cta_rank == 0) mbar_arrive_expect_tx(fb, stage_tx);
             const uint32_t fb_local = fb;
             if constexpr (kCG == 2) fb = mapa_shared(fb, leader_rank);   // the pair's leader owns the full barriers
             const int k_idx = kb * kBlockK;
@@ -434,7 +449,7 @@ siglip_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_consta
               } else {
 #pragma unroll
                 for (int h = 0; h < C::kBRows / 64; ++h)
-                  tma_load_2d<kCG>(tmB, fb, sB + h * 8192, n_idx + 64 * h, k_idx);
+                  if (h * 64 < b_rows) tma_load_2d<kCG>(tmB, fb, sB + h * 8192, n_idx + 64 * h, k_idx);
               }
             } else if constexpr (kCG == 1) {
               // this CTA fetches 1/kMC of the common B tile and multicasts it to every CTA of the cluster
@@ -486,7 +501,7 @@ siglip_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_consta
       for (int t = cluster_id; t < total_tiles; t += num_clusters) {
         const TileCoord tc = decode_tile<kMC>(p, t, mc_rank);
         const Problem& pr = p.prob[tc.prob];
-        const uint32_t idesc = make_idesc_bf16(C::kTileM, kTileN, pr.a_mn, pr.b_mn, pr.ab_f16);
+        const uint32_t idesc = make_idesc_bf16(C::kTileM, tile_cols<kMode, kMC>(pr, tc.n_blk), pr.a_mn, pr.b_mn, pr.ab_f16);
         // K-major: 8-row groups 1024 B apart (SBO), K advance 32 B inside the swizzle row.
         // MN-major: 64-element MN blocks 8192 B apart (LBO), 8-k groups 1024 B apart (SBO), K advance 16 rows.
         const uint32_t a_lbo = pr.a_mn ? 8192u : 16u, b_lbo = pr.b_mn ? 8192u : 16u;
@@ -630,10 +645,14 @@ siglip_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_consta
       // kSlabsPerWarp slabs of 32 columns. With four epilogue warps per SM sub-partition the TMEM load latency
       // of one warp is covered by the arithmetic of the others.
       uint32_t v[32];
+      // column groups beyond a short (128-column) tile have nothing to read (warp-uniform)
+      const bool cols_active = cgrp * kEpiCols < tile_cols<kMode, kMC>(pr, tc.n_blk);
 #pragma unroll
       for (int c = 0; c < kSlabsPerWarp; ++c) {
-        tmem_ld_32x32(taddr + 32 * c, v);
-        tmem_ld_wait();
+        if (cols_active) {
+          tmem_ld_32x32(taddr + 32 * c, v);
+          tmem_ld_wait();
+        }
         if (c == kSlabsPerWarp - 1) {
           // every TMEM read of this warp for this accumulator stage has landed: hand the stage back
           tc_fence_before();
@@ -646,7 +665,7 @@ siglip_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_consta
             }
           }
         }
-        slab(v, c);
+        if (cols_active) slab(v, c);
       }
 
       if constexpr (kMode == kModeLoss) {

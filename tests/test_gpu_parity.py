@@ -73,7 +73,8 @@ def test_mainloop_operand_layouts(cg, amn, bmn, a_f16, monkeypatch):
         monkeypatch.setenv("SIGLIP_DEBUG_AB_F16", "1")
     else:
         monkeypatch.delenv("SIGLIP_DEBUG_AB_F16", raising=False)
-    for (M, N, K) in [(256, 256, 64), (512, 768, 1024), (300, 264, 200), (128, 256, 64), (2000, 520, 328)]:
+    for (M, N, K) in [(256, 256, 64), (512, 768, 1024), (300, 264, 200), (128, 256, 64), (2000, 520, 328),
+                      (512, 384, 256), (640, 1152, 192), (256, 128, 128), (256, 72, 64)]:
         A = torch.randn(M, K, device=dev).to(adt)
         B = torch.randn(N, K, device=dev).to(adt)
         ref = A.float() @ B.float().T
@@ -104,6 +105,30 @@ def test_mainloop_operand_layouts(cg, amn, bmn, a_f16, monkeypatch):
 # ---------------------------------------------------------------------------------------------------------
 # golden fixtures: the reference's own outputs
 # ---------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("cg", [1, 2])
+def test_mainloop_multicast_clusters(cg, monkeypatch):
+    """SIGLIP_OPT_MCAST = 2: clusters of two CTAs (cg 1) or two MMA pairs (cg 2, a 2x2 cluster) share the B tile through
+    TMA multicast; odd tile-row counts leave a fully masked phantom tile."""
+    from distributed_sigmoid_loss_b200 import _capi
+
+    L = _capi.lib()
+    dev = _dev()
+    torch.manual_seed(1)
+    monkeypatch.setenv("SIGLIP_DEBUG_MCAST", "2")
+    monkeypatch.delenv("SIGLIP_DEBUG_AB_F16", raising=False)
+    for (M, N, K, bmn) in [(512, 512, 256, 0), (768, 520, 320, 1), (300, 264, 200, 0), (1300, 1024, 512, 1)]:
+        A = torch.randn(M, K, device=dev).to(torch.bfloat16)
+        B = torch.randn(N, K, device=dev).to(torch.bfloat16)
+        ref = A.float() @ B.float().T
+        Bb = B.T.contiguous() if bmn else B
+        C = torch.full((M, N), float("nan"), device=dev, dtype=torch.float32)
+        rc = L.siglip_debug_gemm(0, cg, M, N, K, A.data_ptr(), K, 0, Bb.data_ptr(), Bb.shape[1], bmn, C.data_ptr(), N,
+                                 torch.cuda.current_stream().cuda_stream)
+        assert rc == 0, _capi.last_error()
+        torch.cuda.synchronize()
+        assert float((C - ref).abs().max()) <= 1e-5 * float(ref.abs().max()) * math.sqrt(K) + 1e-4
+
+
 def _golden_rank_inputs(c, r):
     B = c["batch"]
     img = torch.from_numpy(c["img_all"][r * B:(r + 1) * B]).to(torch.bfloat16).to(_dev()).contiguous()
