@@ -388,7 +388,9 @@ int forward_impl(siglip_ctx* c, const void* img, const void* txt, const float* t
   const size_t chunk_elems = static_cast<size_t>(c->B) * c->D;
   const size_t chunk_bytes = chunk_elems * sizeof(__nv_bfloat16);
   const unsigned int s = ++c->n_fwd;
-  if (save) c->gen = 0;  // the saved state is being overwritten; valid again once everything is enqueued
+  // the saved state is being overwritten (a forward without save still replaces my gathered text slot, which the
+  // backward of a multi-rank job reads for the positive-pair term); valid again once a saving forward is enqueued
+  if (save || c->world > 1) c->gen = 0;
 
   const __nv_bfloat16* own_txt = reinterpret_cast<const __nv_bfloat16*>(txt);
   if (W > 1) {
@@ -422,7 +424,8 @@ int forward_impl(siglip_ctx* c, const void* img, const void* txt, const float* t
   }
   // loss, and (for backward) dt' / dbias for an upstream gradient of 1
   CKI(siglip::launch_finalize(c->partials, c->num_sms, t_prime, 1.0f / static_cast<float>(c->B), loss,
-                              c->scalars + kSavedScalars, c->scalars + kSavedScalars + 1, st));
+                              save ? c->scalars + kSavedScalars : nullptr,
+                              save ? c->scalars + kSavedScalars + 1 : nullptr, st));
   c->launches++;
   if (W > 1) {
     if ((rc = signal_peers(c, 2, s, st))) return rc;
@@ -882,7 +885,7 @@ int siglip_debug_gemm_timed(int device, int cta_group, int M, int N, int K, cons
                             float* ms_per_iter, void* cuda_stream) {
   if (A == nullptr || Bm == nullptr || C == nullptr) return fail(SIGLIP_ERR_INVALID, "null argument");
   if (cta_group != 1 && cta_group != 2) return fail(SIGLIP_ERR_INVALID, "cta_group must be 1 or 2");
-  if (M < 1 || N < 4 || K < 1 || (N % 4) != 0) return fail(SIGLIP_ERR_INVALID, "need N % 4 == 0");
+  if (M < 1 || N < 8 || K < 1 || (N % 8) != 0) return fail(SIGLIP_ERR_INVALID, "need N % 8 == 0");
   if (siglip_device_count() == 0) return fail(SIGLIP_ERR_NO_DEVICE, "no sm_100 device; no CPU fallback");
   CK(cudaSetDevice(device));
   cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);

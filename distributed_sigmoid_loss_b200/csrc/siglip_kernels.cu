@@ -4,17 +4,19 @@
 //     logits = img @ txt_chunk.T * exp(t') + b ; loss = -logsigmoid(labels * logits).sum()
 // and, through autograd, two more contractions (G @ txt, G.T @ img) for the gradients.
 //
-// Here every contraction is a tile loop on the tcgen05 tensor pipe:
-//   * one persistent, warp-specialised kernel (TMA producer warp / single-thread MMA issuer / 8 epilogue warps),
-//   * operands staged by TMA into 128B-swizzled shared memory, accumulators double-buffered in TMEM,
-//   * mode kModeLoss: epilogue turns the S tile into softplus / sigma terms, reduces the three scalar sums and
-//     (training) writes the sigma tile as the bf16 operand of the gradient contractions — the logits never
-//     exist in HBM,
-//   * mode kModeOut: epilogue scales the accumulator by exp(t')/B, adds the fp32 positive-pair rank-1 term and
-//     writes fp32 gradients. Two problems (dimg and dtxt) share one launch so that the tile count fills the
-//     148 SMs evenly.
-// 1-CTA (cta_group::1, 128x256 tiles) and 2-CTA (cta_group::2, 256x256 tiles per SM pair) variants are both
-// instantiated; the host picks one.
+// Here every contraction is a tile loop on the tcgen05 tensor pipe, one persistent warp-specialised kernel template:
+//   * 20 warps: 16 epilogue warps (4 per TMEM lane quarter), a TMA producer warp and an MMA warp (warp-uniform loops,
+//     one elected lane issues), 2 auxiliary warps (TMEM allocation, NVSwitch peer pulls / folds, operand conversion);
+//   * operands staged by TMA into a 128B-swizzled shared-memory ring, 2 x 256-column fp32 accumulators in TMEM so the
+//     MMA of tile n+1 overlaps the epilogue of tile n;
+//   * kModeLoss: the epilogue turns the S tile into softplus / sigma terms, reduces the three scalar sums and
+//     (training) writes the sigma tile as the scaled-fp16 operand of the gradient contractions through TMA stores —
+//     the logits never exist in HBM;
+//   * kModeOut: the epilogue scales the accumulator by grad_out * exp(t') / B, adds the fp32 positive-pair rank-1
+//     term and writes fp32 or bf16 gradients. Two problems (dimg and dtxt) share one launch so that the tile count
+//     fills the 148 SMs evenly.
+// Instantiated for cta_group::1 (128x256 tiles) and cta_group::2 (256x256 tiles per SM pair, the default), each
+// optionally with the B tile TMA-multicast across two vertically adjacent tiles of a cluster.
 #include "siglip_kernels.cuh"
 
 #include <stdio.h>
@@ -39,7 +41,7 @@ constexpr int kNumThreads = (kNumEpiWarps + 4) * 32;
 constexpr int kAccStages = 2;
 constexpr int kTmemCols = 512;
 
-constexpr int kStagingBytesPerWarp = 2048;  // one 32x32 bf16 slab, 64-byte rows, 64B-swizzled (TMA store source)
+constexpr int kStagingBytesPerWarp = 2048;  // one 32x32 16-bit slab, 64-byte rows, 64B-swizzled (TMA store source)
 
 template <int kCG, int kMode, int kStagesT>
 struct Cfg {
@@ -190,7 +192,7 @@ constexpr float kFastZ = -4.2f;  // e < 0.015 < 2^-6: series truncation e^4/5 < 
 // The sigma slab goes to HBM through shared memory + one TMA store per warp: 4 conflict-free 16-byte
 // st.shared per thread instead of 4 strided 16-byte global stores (32 cache lines per instruction).
 struct GStore {
-  const CUtensorMap* tmap;  // bf16 [B, B] tensor, box {32 cols, 32 rows}, SWIZZLE_64B
+  const CUtensorMap* tmap;  // 16-bit [B, B] tensor, box {32 cols, 32 rows}, SWIZZLE_64B
   uint32_t stage;           // this warp's 2 KiB staging buffer (shared::cta address, 512-byte aligned)
   int row0;                 // first row of this warp's 32-row block
   int lane;
@@ -268,7 +270,7 @@ __device__ __forceinline__ void loss_slab(const uint32_t (&v)[32], float t, floa
       if (row == col0 + j) {                           // positive pair (label +1): softplus(-z), -sigma(-z)
         sp = fmaxf(-z, 0.f) + l;
         g = -((z >= 0.f) ? e * r : r);                 // sigma(-z) without the 1 - sigma(z) cancellation
-        g_store = 0.f;                                 // the bf16 operand carries negatives only
+        g_store = 0.f;                                 // the 16-bit operand carries negatives only
         if (store_g && valid) g_diag[row] = g;
       }
     }
@@ -711,7 +713,7 @@ siglip_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_consta
       }
     }
   } else {
-    // ============================ warps 10, 11: NVSwitch peer pull ============================
+    // ===================== the two auxiliary warps: NVSwitch peer pull, conversions, fold =====================
     // The next text chunk is read ONCE from its owner's buffer (P2P over NVLink) into local HBM while this
     // chunk's tiles compute (replaces distributed_utils.py:10-27 neighbour_exchange / the all_gather at
     // distributed_sigmoid_loss.py:35). MMA operands are then fed from local memory only.

@@ -409,6 +409,16 @@ def test_split_forward_backward_and_generation_guard():
     _check("dt' * g", p2, float(dtp) * -1.75, tol=1e-6)
     _check("dbias * g", b2, float(db) * -1.75, tol=1e-6)
     eng.close()
+    # an evaluation forward (no_grad) between forward and backward must not disturb the saved state
+    e0 = _engine(B, D, 2)
+    e0.forward(img, txt, tp, bias, True)
+    e0.forward(img2, txt2, tp, bias, False)
+    d3, t3, p3, b3 = e0.backward(img, txt, tp, None)
+    torch.cuda.synchronize()
+    _check("dimg after an interleaved eval forward", d3, dimg, tol=1e-6)
+    _check("dt' after an interleaved eval forward", p3, float(dtp), tol=1e-6)
+    _check("dbias after an interleaved eval forward", b3, float(db), tol=1e-6)
+    e0.close()
     # two graphs on one module, backward in reverse order
     mod = DDPSigmoidLoss(B).to(_dev())
     a1, a2 = img.clone().requires_grad_(True), img2.clone().requires_grad_(True)
