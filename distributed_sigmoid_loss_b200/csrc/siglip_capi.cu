@@ -273,10 +273,34 @@ int run_loss_chunk(siglip_ctx* c, int k, const void* img, const __nv_bfloat16* t
       p.cvt_n16[1] = n16;
     }
   }
+  unsigned long long* wstats = nullptr;
+  if (getenv("SIGLIP_DEBUG_LOSS_WAITSTATS")) {   // diagnostic: where the roles of the loss kernel spend their cycles
+    CK(cudaMalloc(reinterpret_cast<void**>(&wstats), 8 * 256 * sizeof(unsigned long long)));
+    CK(cudaMemsetAsync(wstats, 0, 8 * 256 * sizeof(unsigned long long), st));
+    p.wait_stats = wstats;
+  }
   if ((rc = timing_mark(c, c->ev_loss, c->ev_loss_used, st))) return rc;
   CKI(siglip::launch_gemm(cg, siglip::kModeLoss, c->stages_loss, mc, &tmA, &tmB, &tmA, &tmB, &tmG, p, c->num_sms,
                           st));
   if ((rc = timing_mark(c, c->ev_loss, c->ev_loss_used, st))) return rc;
+  if (wstats != nullptr) {
+    CK(cudaStreamSynchronize(st));
+    std::vector<unsigned long long> h(8 * 256);
+    CK(cudaMemcpy(h.data(), wstats, h.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    double s[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    int nmma = 0, nall = 0;
+    for (int b = 0; b < 256; ++b) {
+      if (h[8 * b + 7]) nall++;
+      if (h[8 * b + 3]) nmma++;
+      for (int j = 0; j < 8; ++j) s[j] += static_cast<double>(h[8 * b + j]);
+    }
+    printf("[loss waitstats] producer empty-wait %.0f cyc/CTA | MMA (%d issuers): loop %.0f cyc, full-wait %.1f%%, "
+           "tmem-wait (epilogue not done) %.1f%% | epilogue warp 0 (%d CTAs): loop %.0f cyc, waiting for an accumulator %.1f%%\n",
+           s[0] / (nall ? nall : 1), nmma, s[3] / (nmma ? nmma : 1), 100.0 * s[1] / (s[3] > 0 ? s[3] : 1),
+           100.0 * s[2] / (s[3] > 0 ? s[3] : 1), nall, s[7] / (nall ? nall : 1), 100.0 * s[6] / (s[7] > 0 ? s[7] : 1));
+    fflush(stdout);
+    cudaFree(wstats);
+  }
   c->launches++;
   return 0;
 }

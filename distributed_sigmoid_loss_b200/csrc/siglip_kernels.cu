@@ -89,6 +89,15 @@ __device__ __forceinline__ void named_barrier_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
+// sum += x with a running compensation term (Kahan): the error of each fp32 addition is carried into the next one.
+// Written with explicit intrinsics so that fast-math style reassociation cannot remove the compensation.
+__device__ __forceinline__ void kahan_add(float& sum, float& comp, float x) {
+  const float y = __fsub_rn(x, comp);
+  const float t = __fadd_rn(sum, y);
+  comp = __fsub_rn(__fsub_rn(t, sum), y);
+  sum = t;
+}
+
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -184,7 +193,7 @@ __device__ __forceinline__ TileCoord decode_tile(const KernelParams& p, int t, i
 // Sums kept per thread: sum term, sum g, sum g*s (-> loss, dbias, dt').
 //
 // Fast path (whole warp slab has z < kFastZ, i.e. e = exp(z) < 2^-6, which is where a SigLIP batch lives:
-// bias ~ -10): 2 MUFU (ex2, rcp) + 10 FMA-pipe ops per element, log1p by its alternating series.
+// bias ~ -10): 1 MUFU (ex2) + ~6 packed FMA-pipe instructions per element, sigma and log1p by their series.
 // General path: any z, exp(-|z|) + degree-7 log1p polynomial + rcp.
 // -------------------------------------------------------------------------------------------------
 constexpr float kFastZ = -4.2f;  // e < 0.015 < 2^-6: series truncation e^4/5 < 1.1e-8 relative
@@ -221,29 +230,47 @@ __device__ __forceinline__ void store_g_slab(const GStore& gs, int col0, const u
   }
 }
 
+// Fast path: every z of the slab is < kFastZ, so e = exp(z) < 2^-6 and both sigma(z) = e / (1 + e) and log1p(e) are
+// evaluated by their alternating series on the FMA pipe (truncation < 6e-8 relative), two elements per instruction
+// (FFMA2 / FMUL2 / FADD2). One MUFU (ex2) per element instead of two: the epilogue of this kernel is bound by the
+// MUFU and FMA pipes, not by the tensor pipe it has to keep up with.
 template <bool kF16>
 __device__ __forceinline__ void loss_slab_fast(const uint32_t (&v)[32], float tl, float bl, int col0, bool store_g,
                                                const GStore& gst, float gscale, float& acc_sp, float& acc_g,
                                                float& acc_gs) {
   uint32_t packed[16];
-  float g_prev = 0.f;
+  const f32x2 tl2 = pack2(tl, tl), bl2 = pack2(bl, bl), gs2 = pack2(gscale, gscale);
+  const f32x2 one = pack2(1.0f, 1.0f), neg1 = pack2(-1.0f, -1.0f);
+  const f32x2 c3 = pack2(-0.25f, -0.25f), c2 = pack2(0.33333334f, 0.33333334f), c1 = pack2(-0.5f, -0.5f);
+  f32x2 a_sp = pack2(0.f, 0.f), a_g = pack2(0.f, 0.f), a_gs = pack2(0.f, 0.f);
 #pragma unroll
-  for (int j = 0; j < 32; ++j) {
-    const float s = __uint_as_float(v[j]);
-    const float e = ex2_approx(fmaf(s, tl, bl));       // exp(z), z < 0
-    const float g = e * rcp_approx(1.0f + e);           // sigma(z)
-    float p = fmaf(e, -0.25f, 0.33333334f);             // log1p(e) = e*(1 - e*(1/2 - e*(1/3 - e/4)))
-    p = fmaf(-e, p, 0.5f);
-    p = fmaf(-e, p, 1.0f);
-    acc_sp = fmaf(e, p, acc_sp);
-    acc_g += g;
-    acc_gs = fmaf(g, s, acc_gs);
-    if (j & 1) {
-      packed[j >> 1] = pack_16x2<kF16>(g_prev, g * gscale);
-    } else {
-      g_prev = g * gscale;
-    }
+  for (int j = 0; j < 16; ++j) {
+    const f32x2 s = pack2(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1]));
+    const f32x2 t1 = fma2(s, tl2, bl2);                   // z * log2(e)
+    float t1a, t1b;
+    unpack2(t1, t1a, t1b);
+    const f32x2 e = pack2(ex2_approx(t1a), ex2_approx(t1b));   // exp(z), z < kFastZ
+    f32x2 q = fma2(e, neg1, one);                          // sigma(z) / e = 1 - e + e^2 - e^3
+    q = fma2(e, q, neg1);
+    q = fma2(e, q, one);
+    const f32x2 g = mul2(e, q);                            // sigma(z)
+    f32x2 l = fma2(e, c3, c2);                             // log1p(e) / e = 1 - e/2 + e^2/3 - e^3/4
+    l = fma2(e, l, c1);
+    l = fma2(e, l, one);
+    a_sp = fma2(e, l, a_sp);
+    a_g = add2(a_g, g);
+    a_gs = fma2(g, s, a_gs);
+    float g0, g1;
+    unpack2(mul2(g, gs2), g0, g1);
+    packed[j] = pack_16x2<kF16>(g0, g1);
   }
+  float x0, x1;
+  unpack2(a_sp, x0, x1);
+  acc_sp += x0 + x1;
+  unpack2(a_g, x0, x1);
+  acc_g += x0 + x1;
+  unpack2(a_gs, x0, x1);
+  acc_gs += x0 + x1;
   if (store_g) store_g_slab(gst, col0, packed);
 }
 
@@ -582,7 +609,11 @@ siglip_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_consta
     const float t_exact = expf(*p.t_prime);
     const float bias = (kMode == kModeLoss) ? *p.bias : 0.f;
     const float tl = t_exact * kLog2e, bl = bias * kLog2e;
-    double d_sp = 0.0, d_g = 0.0, d_gs = 0.0;
+    // per-thread running sums over the tiles of this CTA: compensated fp32 (Kahan) — a DADD per sum, thread and tile
+    // was 11 % of the loss kernel's stall samples (the fp64 pipe of this part is narrow); fp64 only at the very end
+    float s_sp = 0.f, s_g = 0.f, s_gs = 0.f, c_sp = 0.f, c_g = 0.f, c_gs = 0.f;
+    long long w_epi = 0;
+    const long long epi_start = clock_cycles();
     int as = 0;
     uint32_t aphase = 0;
     uint32_t empty_remote[kAccStages];
@@ -595,7 +626,8 @@ siglip_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_consta
       const Problem& pr = p.prob[tc.prob];
       const int row = tc.m_blk * C::kTileM + static_cast<int>(cta_rank) * kBlockM + row_in_cta;
       const int col_base = tc.n_blk * kTileN + cgrp * kEpiCols;
-      mbar_wait(tmem_full_bar(as), aphase, p.dbg, 4, t, as, p.epi_sleep_ns);
+      mbar_wait(tmem_full_bar(as), aphase, p.dbg, 4, t, as, p.epi_sleep_ns,
+                (p.wait_stats != nullptr && warp == 0) ? &w_epi : nullptr);
       tc_fence_after();
       const uint32_t taddr = tmem_base + static_cast<uint32_t>(as * kTileN + cgrp * kEpiCols) +
                              (static_cast<uint32_t>(q * 32) << 16);
@@ -661,9 +693,9 @@ siglip_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_consta
           __syncwarp();
           if (lane == 0) {
             if (kCG == 2 && cta_rank != 0) {
-              mbar_arrive_cluster(empty_remote[as]);
+              mbar_arrive_cluster_relaxed(empty_remote[as]);
             } else {
-              mbar_arrive(tmem_empty_bar(as));
+              mbar_arrive_relaxed(tmem_empty_bar(as));
             }
           }
         }
@@ -671,22 +703,26 @@ siglip_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_consta
       }
 
       if constexpr (kMode == kModeLoss) {
-        d_sp += static_cast<double>(acc_sp);
-        d_g += static_cast<double>(acc_g);
-        d_gs += static_cast<double>(acc_gs);
+        kahan_add(s_sp, c_sp, acc_sp);
+        kahan_add(s_g, c_g, acc_g);
+        kahan_add(s_gs, c_gs, acc_gs);
       }
       if (++as == kAccStages) {
         as = 0;
         aphase ^= 1u;
       }
     }
+    if (p.wait_stats != nullptr && threadIdx.x == 0) {
+      p.wait_stats[8ll * blockIdx.x + 6] = static_cast<unsigned long long>(w_epi);
+      p.wait_stats[8ll * blockIdx.x + 7] = static_cast<unsigned long long>(clock_cycles() - epi_start);
+    }
     if constexpr (kMode == kModeLoss) {
       // all sigma slabs of this warp must be in global memory before the kernel ends
       if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
       // fixed-order reduction: lanes -> warp -> epilogue warps -> one slot per CTA (summed later in slot order)
-      d_sp = warp_sum(d_sp);
-      d_g = warp_sum(d_g);
-      d_gs = warp_sum(d_gs);
+      double d_sp = warp_sum(static_cast<double>(s_sp) - static_cast<double>(c_sp));
+      double d_g = warp_sum(static_cast<double>(s_g) - static_cast<double>(c_g));
+      double d_gs = warp_sum(static_cast<double>(s_gs) - static_cast<double>(c_gs));
       double* red = reinterpret_cast<double*>(smem_raw + (red_smem - smem_u32(smem_raw)));
       if (lane == 0) {
         red[warp * 3 + 0] = d_sp;
