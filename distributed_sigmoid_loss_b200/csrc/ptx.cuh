@@ -344,6 +344,13 @@ __device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) {
 // ---------------------------------------------------------------------------------------------
 // MUFU approximations (each one SFU instruction)
 // ---------------------------------------------------------------------------------------------
+// three-input maximum (FMNMX3 on sm_100)
+__device__ __forceinline__ float max3(float a, float b, float c) {
+  float d;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+  return d;
+}
+
 __device__ __forceinline__ float ex2_approx(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));

@@ -109,7 +109,11 @@ constexpr int kMaxWorld = 32;
 // flags[kind][rank]: counters written by peers with st.release.sys
 //   0 text of forward #n is in place        1 dtxt contribution of backward #n, gradient slot j is complete
 //   2 forward #n finished pulling everyone's text     3 backward #n finished reading everyone's contributions
-constexpr int kFlagKinds = 4;
+//   4 (dt', dbias) of backward #n are in the owner's mailbox (SIGLIP_OPT_SYNC_SCALAR_GRADS)
+constexpr int kFlagKinds = 5;
+// the mailbox (2 floats) lives behind the flag counters, in the same peer-mapped allocation
+constexpr int kMailboxOffset = kFlagKinds * kMaxWorld;
+constexpr size_t kFlagBytes = (kMailboxOffset + 4) * sizeof(unsigned int);
 
 struct IpcBlob {
   cudaIpcMemHandle_t txt;
@@ -136,6 +140,7 @@ struct siglip_ctx {
   int grad_bf16 = 0;                     // dimg / dtxt outputs are bf16 instead of fp32
   int epi_sleep_grad_ns = 0;             // back-off of the gradient kernel's epilogue warps while a K loop runs
   int epi_sleep_loss_ns = 0;
+  int sync_scalar_grads = 0;             // backward returns the mean over ranks of dt' / dbias
   // workspaces
   __nv_bfloat16* txt_all = nullptr;      // [world][B, D] bf16; slot `rank` is what the peers pull (world > 1)
   __nv_bfloat16* G[kMaxWorld] = {};      // per step k: [Bp, Bp] sigma operand (fp16 bits x kGScale), diagonal zeroed
@@ -157,6 +162,7 @@ struct siglip_ctx {
   const float** reduce_ptrs_dev = nullptr;   // [world] peer_slots[p] + rank*B*D  (reduction-at-the-end variant)
   const float** final_ptrs_dev = nullptr;    // [2] {dtxt_acc, own slot}: the local last add of the progressive variant
   unsigned int** signal_ptrs_dev = nullptr;  // [kFlagKinds][world]
+  const float** mailbox_ptrs_dev = nullptr;  // [world] every rank's (dt', dbias) mailbox
   unsigned int n_fwd = 0, n_bwd = 0;         // forward / backward passes issued (flag counters)
   unsigned long long gen = 0;                // generation of the state saved for backward (0 = none)
   DebugRecord* dbg_host = nullptr;
@@ -524,7 +530,15 @@ int backward_impl(siglip_ctx* c, const void* img, const void* txt, const float* 
     c->launches++;
     if ((rc = signal_peers(c, 3, n, st))) return rc;
   }
-  if (dt_prime != nullptr || dbias != nullptr) {
+  if (W > 1 && c->sync_scalar_grads) {
+    // a collective: issued on every rank whether or not this caller wants the two values. My mailbox is free again:
+    // every peer has signalled the text of a later forward, i.e. finished the backward that read it.
+    CKI(siglip::launch_allreduce_scalars(c->scalars + kSavedScalars, grad_out,
+                                         reinterpret_cast<float*>(c->flags + kMailboxOffset), c->mailbox_ptrs_dev,
+                                         c->signal_ptrs_dev + 4 * W, c->flags + 4 * kMaxWorld, W, n, dt_prime, dbias,
+                                         c->dbg_dev, st));
+    c->launches++;
+  } else if (dt_prime != nullptr || dbias != nullptr) {
     CKI(siglip::launch_scale_scalars(c->scalars + kSavedScalars, grad_out, dt_prime, dbias, st));
     c->launches++;
   }
@@ -588,9 +602,9 @@ int siglip_ctx_create(siglip_ctx** out, int device, int rank, int world, int B, 
   CK(alloc(reinterpret_cast<void**>(&c->img16), chunk_elems * sizeof(__nv_bfloat16)));
   CK(alloc(reinterpret_cast<void**>(&c->txt16), chunk_elems * world * sizeof(__nv_bfloat16)));
   CK(alloc(reinterpret_cast<void**>(&c->partials), static_cast<size_t>(c->num_sms) * 4 * sizeof(double)));
-  CK(alloc(reinterpret_cast<void**>(&c->flags), kFlagKinds * kMaxWorld * sizeof(unsigned int)));
+  CK(alloc(reinterpret_cast<void**>(&c->flags), kFlagBytes));
   CK(alloc(reinterpret_cast<void**>(&c->scalars), 16 * sizeof(float)));
-  CK(cudaMemset(c->flags, 0, kFlagKinds * kMaxWorld * sizeof(unsigned int)));
+  CK(cudaMemset(c->flags, 0, kFlagBytes));
   CK(cudaMemset(c->partials, 0, static_cast<size_t>(c->num_sms) * 4 * sizeof(double)));
   CK(cudaMemset(c->g_diag, 0, static_cast<size_t>(c->Bp) * sizeof(float)));
   CK(cudaMemset(c->scalars, 0, 16 * sizeof(float)));
@@ -602,6 +616,7 @@ int siglip_ctx_create(siglip_ctx** out, int device, int rank, int world, int B, 
     CK(alloc(reinterpret_cast<void**>(&c->reduce_ptrs_dev), world * sizeof(float*)));
     CK(alloc(reinterpret_cast<void**>(&c->final_ptrs_dev), 2 * sizeof(float*)));
     CK(alloc(reinterpret_cast<void**>(&c->signal_ptrs_dev), kFlagKinds * world * sizeof(unsigned int*)));
+    CK(alloc(reinterpret_cast<void**>(&c->mailbox_ptrs_dev), world * sizeof(float*)));
     const float* fin[2] = {c->dtxt_acc, c->slots + rank * chunk_elems};
     CK(cudaMemcpy(c->final_ptrs_dev, fin, sizeof(fin), cudaMemcpyHostToDevice));
   }
@@ -644,6 +659,9 @@ int siglip_ctx_set_option(siglip_ctx* c, int option, int value) {
       return 0;
     case SIGLIP_OPT_EPI_SLEEP_LOSS_NS:
       c->epi_sleep_loss_ns = value < 0 ? 0 : value;
+      return 0;
+    case SIGLIP_OPT_SYNC_SCALAR_GRADS:
+      c->sync_scalar_grads = value ? 1 : 0;
       return 0;
     case SIGLIP_OPT_STAGES_LOSS:
       c->stages_loss = value;
@@ -692,6 +710,9 @@ static int publish_peer_tables(siglip_ctx* c) {
     for (int p = 0; p < c->world; ++p)
       sig[k * c->world + p] = c->peer_flags[p] + k * kMaxWorld + (c->loopback ? p : c->rank);
   CK(cudaMemcpy(c->signal_ptrs_dev, sig.data(), sig.size() * sizeof(unsigned int*), cudaMemcpyHostToDevice));
+  std::vector<const float*> mb(c->world);
+  for (int p = 0; p < c->world; ++p) mb[p] = reinterpret_cast<const float*>(c->peer_flags[p] + kMailboxOffset);
+  CK(cudaMemcpy(c->mailbox_ptrs_dev, mb.data(), c->world * sizeof(float*), cudaMemcpyHostToDevice));
   c->peers_ready = true;
   return 0;
 }
@@ -1041,6 +1062,7 @@ void siglip_ctx_destroy(siglip_ctx* c) {
   cudaFree(c->scalars);
   cudaFree(c->reduce_ptrs_dev);
   cudaFree(c->signal_ptrs_dev);
+  cudaFree(c->mailbox_ptrs_dev);
   cudaFree(c->h_img);
   cudaFree(c->h_txt);
   cudaFree(c->h_dimg);

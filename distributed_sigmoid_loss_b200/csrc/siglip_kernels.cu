@@ -239,8 +239,10 @@ __device__ __forceinline__ void loss_slab_fast(const uint32_t (&v)[32], float tl
                                                const GStore& gst, float gscale, float& acc_sp, float& acc_g,
                                                float& acc_gs) {
   uint32_t packed[16];
-  const f32x2 tl2 = pack2(tl, tl), bl2 = pack2(bl, bl), gs2 = pack2(gscale, gscale);
-  const f32x2 one = pack2(1.0f, 1.0f), neg1 = pack2(-1.0f, -1.0f);
+  const f32x2 tl2 = pack2(tl, tl), bl2 = pack2(bl, bl);
+  // sigma is produced already multiplied by the power-of-two scale of the 16-bit operand (exact), and the two sums
+  // that use it are un-scaled once per slab
+  const f32x2 gs_p = pack2(gscale, gscale), gs_n = pack2(-gscale, -gscale), one = pack2(1.0f, 1.0f);
   const f32x2 c3 = pack2(-0.25f, -0.25f), c2 = pack2(0.33333334f, 0.33333334f), c1 = pack2(-0.5f, -0.5f);
   f32x2 a_sp = pack2(0.f, 0.f), a_g = pack2(0.f, 0.f), a_gs = pack2(0.f, 0.f);
 #pragma unroll
@@ -250,10 +252,10 @@ __device__ __forceinline__ void loss_slab_fast(const uint32_t (&v)[32], float tl
     float t1a, t1b;
     unpack2(t1, t1a, t1b);
     const f32x2 e = pack2(ex2_approx(t1a), ex2_approx(t1b));   // exp(z), z < kFastZ
-    f32x2 q = fma2(e, neg1, one);                          // sigma(z) / e = 1 - e + e^2 - e^3
-    q = fma2(e, q, neg1);
-    q = fma2(e, q, one);
-    const f32x2 g = mul2(e, q);                            // sigma(z)
+    f32x2 q = fma2(e, gs_n, gs_p);                         // S sigma(z) / e = S (1 - e + e^2 - e^3)
+    q = fma2(e, q, gs_n);
+    q = fma2(e, q, gs_p);
+    const f32x2 g = mul2(e, q);                            // S sigma(z)
     f32x2 l = fma2(e, c3, c2);                             // log1p(e) / e = 1 - e/2 + e^2/3 - e^3/4
     l = fma2(e, l, c1);
     l = fma2(e, l, one);
@@ -261,16 +263,17 @@ __device__ __forceinline__ void loss_slab_fast(const uint32_t (&v)[32], float tl
     a_g = add2(a_g, g);
     a_gs = fma2(g, s, a_gs);
     float g0, g1;
-    unpack2(mul2(g, gs2), g0, g1);
+    unpack2(g, g0, g1);
     packed[j] = pack_16x2<kF16>(g0, g1);
   }
+  const float inv_s = 1.0f / gscale;
   float x0, x1;
   unpack2(a_sp, x0, x1);
   acc_sp += x0 + x1;
   unpack2(a_g, x0, x1);
-  acc_g += x0 + x1;
+  acc_g = fmaf(x0 + x1, inv_s, acc_g);
   unpack2(a_gs, x0, x1);
-  acc_gs += x0 + x1;
+  acc_gs = fmaf(x0 + x1, inv_s, acc_gs);
   if (store_g) store_g_slab(gst, col0, packed);
 }
 
@@ -655,9 +658,9 @@ siglip_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_consta
           const bool sg = p.store_g != 0;
           if (!edge && !diag) {
             // z is monotone in s (t > 0): the slab is "all very negative" iff max s is
-            float smax = __uint_as_float(v[0]);
+            float smax = fmaxf(__uint_as_float(v[0]), __uint_as_float(v[1]));
 #pragma unroll
-            for (int j = 1; j < 32; ++j) smax = fmaxf(smax, __uint_as_float(v[j]));
+            for (int j = 2; j < 32; j += 2) smax = max3(smax, __uint_as_float(v[j]), __uint_as_float(v[j + 1]));
             const bool fast = __all_sync(0xffffffffu, fmaf(smax, t_exact, bias) < kFastZ);
             if (fast)
               loss_slab_fast<true>(v, tl, bl, col0, sg, gst, p.g_scale, acc_sp, acc_g, acc_gs);
@@ -956,6 +959,66 @@ __global__ void wait_flags_kernel(const volatile unsigned int* flags, int n, uns
   }
 }
 
+// Mean over the ranks of the two scalar gradients: what wrapping the module in DDP (README.md:20) or
+// the toy average_gradients (test_distributed_sigmoid_loss.py:79-83) does with an all_reduce, here as one warp that
+// publishes (dt', dbias) in a peer-visible mailbox, signals every rank, waits for every rank and adds the W mailboxes
+// in rank order — the same order on every rank, so all ranks end up with bit-identical parameter gradients.
+__global__ void allreduce_scalars_kernel(const float* __restrict__ saved, const float* __restrict__ g,
+                                         float* mailbox_local, const float* const* __restrict__ mailboxes,
+                                         unsigned int* const* __restrict__ signal_ptrs,
+                                         const volatile unsigned int* flags_local, int world, unsigned int value,
+                                         float* dt_prime, float* dbias, DebugRecord* dbg) {
+  __shared__ float sh[2][32];
+  const int i = threadIdx.x;
+  const float s = (g != nullptr) ? *g : 1.0f;
+  if (i == 0) {
+    asm volatile("st.relaxed.sys.global.f32 [%0], %1;" ::"l"(mailbox_local), "f"(saved[0] * s) : "memory");
+    asm volatile("st.relaxed.sys.global.f32 [%0], %1;" ::"l"(mailbox_local + 1), "f"(saved[1] * s) : "memory");
+    __threadfence_system();
+  }
+  __syncwarp();
+  if (i < world) {
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(signal_ptrs[i]), "r"(value) : "memory");
+    uint64_t t0 = 0;
+    uint32_t spins = 0;
+    while (true) {
+      unsigned int v;
+      asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(flags_local + i) : "memory");
+      if (v >= value) break;
+      if ((++spins & 0xffu) == 0) {
+        const uint64_t now = globaltimer_ns();
+        if (t0 == 0) t0 = now;
+        if (now - t0 > 20000000000ull) {
+          if (dbg != nullptr) {
+            dbg->block = i;
+            dbg->aux0 = v;
+            dbg->aux1 = value;
+            dbg->code = 7;
+            __threadfence_system();
+          }
+          __trap();
+        }
+      }
+    }
+    float a, b;
+    asm volatile("ld.relaxed.sys.global.f32 %0, [%1];" : "=f"(a) : "l"(mailboxes[i]) : "memory");
+    asm volatile("ld.relaxed.sys.global.f32 %0, [%1];" : "=f"(b) : "l"(mailboxes[i] + 1) : "memory");
+    sh[0][i] = a;
+    sh[1][i] = b;
+  }
+  __syncwarp();
+  if (i == 0) {
+    float a = 0.0f, b = 0.0f;
+    for (int p = 0; p < world; ++p) {
+      a += sh[0][p];
+      b += sh[1][p];
+    }
+    const float inv_w = 1.0f / static_cast<float>(world);
+    if (dt_prime) *dt_prime = a * inv_w;
+    if (dbias) *dbias = b * inv_w;
+  }
+}
+
 // -------------------------------------------------------------------------------------------------
 // L2 normalisation fused around the loss (the step the reference's callers run right before it,
 // test_distributed_sigmoid_loss.py:99-101). One warp per row; HBM-bound: coalesced 16-byte accesses, fp32 math.
@@ -1241,6 +1304,15 @@ int launch_normalize_bwd(const void* x, int in_bf16, const float* inv_norm, cons
 int launch_scale(const void* src, void* dst, int is_bf16, const float* g, size_t nbytes, int num_sms,
                  cudaStream_t stream) {
   scale_kernel<<<num_sms * 4, 256, 0, stream>>>(src, dst, is_bf16, g, nbytes / 16);
+  return static_cast<int>(cudaGetLastError());
+}
+
+int launch_allreduce_scalars(const float* saved, const float* g, float* mailbox_local, const float* const* mailboxes_dev,
+                             unsigned int* const* signal_ptrs_dev, const volatile unsigned int* flags_local, int world,
+                             unsigned int value, float* dt_prime, float* dbias, DebugRecord* dbg,
+                             cudaStream_t stream) {
+  allreduce_scalars_kernel<<<1, 32, 0, stream>>>(saved, g, mailbox_local, mailboxes_dev, signal_ptrs_dev, flags_local,
+                                                 world, value, dt_prime, dbias, dbg);
   return static_cast<int>(cudaGetLastError());
 }
 

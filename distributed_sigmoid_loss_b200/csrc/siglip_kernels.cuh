@@ -115,6 +115,9 @@ int launch_scale(const void* src, void* dst, int is_bf16, const float* g, size_t
                  cudaStream_t stream);
 
 // cross-rank flag helpers (peer-mapped pointers)
+int launch_allreduce_scalars(const float* saved, const float* g, float* mailbox_local, const float* const* mailboxes_dev,
+                             unsigned int* const* signal_ptrs_dev, const volatile unsigned int* flags_local, int world,
+                             unsigned int value, float* dt_prime, float* dbias, DebugRecord* dbg, cudaStream_t stream);
 int launch_signal_flags(unsigned int* const* flag_ptrs_dev, int n, unsigned int value, cudaStream_t stream);
 int launch_wait_flags(const volatile unsigned int* flags, int n, unsigned int value, DebugRecord* dbg,
                       cudaStream_t stream);

@@ -311,8 +311,9 @@ class _SigmoidLossFn(torch.autograd.Function):
 
 
 class _EngineCache:
-    def __init__(self, group=None, cta_group: int = 2, overlap_pull: bool = True):
+    def __init__(self, group=None, cta_group: int = 2, overlap_pull: bool = True, sync_scalar_grads: bool = False):
         self.group, self.cta_group, self.overlap_pull = group, cta_group, overlap_pull
+        self.sync_scalar_grads = sync_scalar_grads
         self._engines: Dict[Tuple[int, int, int], SigmoidLossEngine] = {}
 
     def get(self, batch: int, dim: int, device: torch.device) -> SigmoidLossEngine:
@@ -321,6 +322,8 @@ class _EngineCache:
         if eng is None:
             dev = torch.device("cuda", key[0])
             eng = SigmoidLossEngine(batch, dim, dev, self.group, self.cta_group, self.overlap_pull)
+            if self.sync_scalar_grads:
+                eng.set_option(_capi.SIGLIP_OPT_SYNC_SCALAR_GRADS, 1)
             self._engines[key] = eng
         return eng
 
@@ -353,14 +356,18 @@ class DDPSigmoidLoss(nn.Module):
     """
 
     def __init__(self, gpu_batch_size: int, group=None, cta_group: int = 2, overlap_pull: bool = True,
-                 normalize_inputs: bool = False) -> None:
+                 normalize_inputs: bool = False, sync_scalar_grads: bool = False) -> None:
         super().__init__()
         self.t_prime = nn.Parameter(torch.tensor(math.log(10), dtype=torch.float64))
         self.bias = nn.Parameter(torch.tensor(-10.0))
         self.gpu_batch_size = gpu_batch_size
         # extension: take raw encoder outputs and fuse F.normalize (and its backward) around the loss
         self.normalize_inputs = normalize_inputs
-        self._cache = _EngineCache(group, cta_group, overlap_pull)
+        # extension: t_prime.grad / bias.grad come back averaged over the ranks (what DDP's all-reduce
+        # of the two parameters would give, README.md:20), so the module needs no DDP wrapper of its own. Collective:
+        # every rank must set it, and every rank's backward must run.
+        self.sync_scalar_grads = sync_scalar_grads
+        self._cache = _EngineCache(group, cta_group, overlap_pull, sync_scalar_grads)
 
     def engine_for(self, batch: int, dim: int, device: torch.device) -> SigmoidLossEngine:
         return self._cache.get(batch, dim, device)

@@ -43,6 +43,10 @@ enum {
   SIGLIP_OPT_OVERLAP_REDUCE = 8, /* 1 (default): fold the peers' dtxt contributions in step by step inside the gradient kernels; 0: one reduction at the end */
   SIGLIP_OPT_EPI_SLEEP_GRAD_NS = 9, /* nanosleep back-off of the epilogue warps while they wait for an accumulator (gradient kernel) */
   SIGLIP_OPT_EPI_SLEEP_LOSS_NS = 10, /* ... (loss kernel) */
+  SIGLIP_OPT_SYNC_SCALAR_GRADS = 11, /* 1: siglip_backward returns the MEAN over ranks of dt_prime / dbias (what DDP's
+                                        all-reduce of the two parameters does, README.md:20,
+                                        test_distributed_sigmoid_loss.py:79-83), exchanged through peer memory by a
+                                        one-warp kernel; bit-identical on every rank. Collective: set on all ranks */
   SIGLIP_OPT_GRAD_BF16 = 7     /* 1: siglip_fwd_bwd writes dimg / dtxt as bf16 [B, D] (the dtype autograd returns for bf16 inputs); default 0 = fp32 */
 };
 

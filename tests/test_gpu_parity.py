@@ -487,3 +487,24 @@ def test_kernel_launch_accounting():
     lm, ln, gm, gn = eng.kernel_times()
     assert ln == 1 and gn == 1 and lm > 0 and gm > 0
     eng.close()
+
+
+def test_scalar_gradient_mean_option_loopback():
+    """SIGLIP_OPT_SYNC_SCALAR_GRADS on a loopback context (every 'peer' mailbox is my own): the one-warp exchange runs
+    its full signal / wait / gather protocol and the mean of W copies equals the local value, step after step.
+    (Real peers: tools/multi_gpu_check.py.)"""
+    from distributed_sigmoid_loss_b200 import _capi
+    B, D, W = 256, 128, 3
+    img, txt = _synth(B, D, seed=5)
+    tp, b = _scal(math.log(10.0)), _scal(-10.0)
+    eng = _engine(B, D, 2, rank_world=(1, W), loopback=True)
+    for k in range(W):
+        eng.debug_set_text_chunk(k, _synth(B, D, seed=20 + k)[1])
+    _, _, _, dtp0, db0 = eng.fwd_bwd(img, txt, tp, b)
+    eng.set_option(_capi.SIGLIP_OPT_SYNC_SCALAR_GRADS, 1)
+    for _ in range(3):
+        _, _, _, dtp1, db1 = eng.fwd_bwd(img, txt, tp, b)
+        torch.cuda.synchronize()
+        assert abs(float(dtp1) - float(dtp0)) <= 1e-6 * abs(float(dtp0))
+        assert abs(float(db1) - float(db0)) <= 1e-6 * abs(float(db0))
+    eng.close()

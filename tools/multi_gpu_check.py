@@ -112,6 +112,24 @@ def main() -> int:
         dtp=abs(float(dtp) - ref["dt_prime"]) / abs(ref["dt_prime"]),
         db=abs(float(db) - ref["dbias"]) / abs(ref["dbias"])))
 
+    # ---- mean over ranks of the scalar gradients inside the backward (no DDP wrapper needed) -----
+    both = torch.stack([dtp.reshape(()), db.reshape(())]).double()
+    dist.all_reduce(both)
+    both /= world
+    eng.set_option(_capi.SIGLIP_OPT_SYNC_SCALAR_GRADS, 1)
+    for rep in range(3):
+        _, _, _, dtp_m, db_m = eng.fwd_bwd(img, txt, torch.tensor([tp], device=dev), torch.tensor([bias], device=dev))
+        torch.cuda.synchronize()
+        mine = torch.stack([dtp_m.reshape(()), db_m.reshape(())])
+        gathered = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(gathered, mine)
+        identical = all(torch.equal(gathered[0], x) for x in gathered)
+        report(f"scalar-grad mean rep{rep}", dict(
+            dtp=abs(float(dtp_m) - float(both[0])) / abs(float(both[0])),
+            db=abs(float(db_m) - float(both[1])) / abs(float(both[1])),
+            not_bit_identical=0.0 if identical else 1.0), tol=1e-5)
+    eng.set_option(_capi.SIGLIP_OPT_SYNC_SCALAR_GRADS, 0)
+
     # ---- timing at the headline per-rank shape -------------------------------------------------------------
     if args.time:
         B, D = args.batch, args.dim
