@@ -186,10 +186,23 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
+    if "LOCAL_RANK" in os.environ:
+        # under torchrun: the launcher exports OMP_NUM_THREADS=1 for its workers; the CPU arm is meant to use every
+        # host thread, so rank 0 re-runs itself in a clean environment and relays the line
+        env = {k: v for k, v in os.environ.items()
+               if k not in ("RANK", "LOCAL_RANK", "WORLD_SIZE", "OMP_NUM_THREADS", "MASTER_ADDR", "MASTER_PORT",
+                            "GROUP_RANK", "ROLE_RANK", "LOCAL_WORLD_SIZE", "ROLE_WORLD_SIZE", "GROUP_WORLD_SIZE")}
+        out = subprocess.run([sys.executable, os.path.abspath(__file__)] + sys.argv[1:], env=env, capture_output=True,
+                             text=True)
+        sys.stderr.write(out.stderr[-2000:])
+        sys.stdout.write(out.stdout)
+        sys.stdout.flush()
+        return out.returncode
     import torch
 
     B, D, W = args.batch, args.dim, args.gpus
-    rows = args.cpu_sample_rows
+    # bounded sample: about one second of host work per step at every N (the W text chunks are all scored)
+    rows = min(B, max(128, args.cpu_sample_rows // W))
     value, sec, threads = cpu_reference_rate(B, D, W, rows, max(1, args.steps), max(0, args.warmup))
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
