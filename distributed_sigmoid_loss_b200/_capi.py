@@ -62,6 +62,7 @@ SIGLIP_OPT_OVERLAP_REDUCE = 8
 SIGLIP_OPT_EPI_SLEEP_GRAD_NS = 9
 SIGLIP_OPT_EPI_SLEEP_LOSS_NS = 10
 SIGLIP_OPT_SYNC_SCALAR_GRADS = 11
+SIGLIP_OPT_BIDIR = 12
 
 _lib: Optional[ctypes.CDLL] = None
 

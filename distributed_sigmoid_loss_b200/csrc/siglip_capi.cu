@@ -141,6 +141,7 @@ struct siglip_ctx {
   int epi_sleep_grad_ns = 0;             // back-off of the gradient kernel's epilogue warps while a K loop runs
   int epi_sleep_loss_ns = 0;
   int sync_scalar_grads = 0;             // backward returns the mean over ranks of dt' / dbias
+  int bidir = 0;                         // visiting order of the text chunks: r, r+1, r-1, r+2, r-2, ...
   // workspaces
   __nv_bfloat16* txt_all = nullptr;      // [world][B, D] bf16; slot `rank` is what the peers pull (world > 1)
   __nv_bfloat16* G[kMaxWorld] = {};      // per step k: [Bp, Bp] sigma operand (fp16 bits x kGScale), diagonal zeroed
@@ -382,6 +383,17 @@ int run_grad_chunk(siglip_ctx* c, int k, const void* img, const __nv_bfloat16* t
   return 0;
 }
 
+// Owner of the text chunk a rank scores at step k. Unidirectional: r, r+1, r+2, ... (the pairs of the reference's ring,
+// rwightman_sigmoid_loss.py:108-122). Bidirectional: r, r+1, r-1, r+2, r-2, ... (the order of its bidir exchange,
+// rwightman_sigmoid_loss.py:75-107). At every step each owner is read by exactly one rank either way.
+inline int step_offset(const siglip_ctx* c, int k) {
+  if (!c->bidir) return k;
+  return (k & 1) ? (k + 1) / 2 : -(k / 2);
+}
+inline int step_owner(const siglip_ctx* c, int rank, int k) {
+  return ((rank + step_offset(c, k)) % c->world + c->world) % c->world;
+}
+
 int signal_peers(siglip_ctx* c, int kind, unsigned int value, cudaStream_t st) {
   CKI(siglip::launch_signal_flags(c->signal_ptrs_dev + kind * c->world, c->world, value, st));
   c->launches++;
@@ -433,11 +445,11 @@ int forward_impl(siglip_ctx* c, const void* img, const void* txt, const float* t
   CKI(siglip::launch_zero_partials(c->partials, c->num_sms, st));
   c->launches++;
   for (int k = 0; k < W; ++k) {
-    const int cidx = (r + k) % W;
+    const int cidx = step_owner(c, r, k);
     const __nv_bfloat16* txt_c = (k == 0) ? own_txt : c->txt_all + cidx * chunk_elems;
     PullJob pull;
     if (k + 1 < W) {
-      const int nxt = (r + k + 1) % W;
+      const int nxt = step_owner(c, r, k + 1);
       pull.src = c->peer_txt[nxt] + nxt * chunk_elems;
       pull.dst = c->txt_all + nxt * chunk_elems;
       pull.bytes = chunk_bytes;
@@ -497,7 +509,7 @@ int backward_impl(siglip_ctx* c, const void* img, const void* txt, const float* 
       (W > 1) ? c->txt_all + r * chunk_elems : reinterpret_cast<const __nv_bfloat16*>(txt);
   for (int j = 1; j <= W; ++j) {
     const int k = (j < W) ? j : 0;
-    const int cidx = (r + k) % W;
+    const int cidx = step_owner(c, r, k);
     const bool last = (j == W);
     const __nv_bfloat16* txt_c = (k == 0) ? own_txt : nullptr;
     const float* dimg_add = (j > 1) ? c->dimg_acc : nullptr;
@@ -505,8 +517,8 @@ int backward_impl(siglip_ctx* c, const void* img, const void* txt, const float* 
     void* dtxt_out = (W == 1) ? dtxt : static_cast<void*>(c->slots + cidx * chunk_elems);
     FoldJob fold;
     if (W > 1 && c->overlap_reduce && j >= 2) {
-      // the contribution rank p = r - (j-1) produced for me in ITS gradient slot j-1
-      const int pr = ((r - (j - 1)) % W + W) % W;
+      // the contribution for me that rank p = r - offset(j-1) produced in ITS gradient slot j-1
+      const int pr = ((r - step_offset(c, j - 1)) % W + W) % W;
       fold.in = (j == 2) ? nullptr : c->dtxt_acc;
       fold.remote = c->peer_slots[pr] + r * chunk_elems;
       fold.flag = c->flags + 1 * kMaxWorld + pr;
@@ -659,6 +671,10 @@ int siglip_ctx_set_option(siglip_ctx* c, int option, int value) {
       return 0;
     case SIGLIP_OPT_EPI_SLEEP_LOSS_NS:
       c->epi_sleep_loss_ns = value < 0 ? 0 : value;
+      return 0;
+    case SIGLIP_OPT_BIDIR:
+      c->bidir = value ? 1 : 0;
+      c->gen = 0;   // a saved forward was laid out in the other order
       return 0;
     case SIGLIP_OPT_SYNC_SCALAR_GRADS:
       c->sync_scalar_grads = value ? 1 : 0;

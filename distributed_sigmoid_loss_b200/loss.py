@@ -29,12 +29,18 @@ def _group_rank_world(group) -> Tuple[int, int]:
     return 0, 1
 
 
-def chunk_schedule(rank: int, world: int):
-    """Order in which a rank scores its images against the text chunks: own chunk first, then the chunks of
-    ranks rank+1, rank+2, ... (mod world). Same visiting order as the reference's unidirectional ring
+def chunk_schedule(rank: int, world: int, bidir: bool = False):
+    """Order in which a rank scores its images against the text chunks (owner rank per step), own chunk first.
+    bidir=False: rank+1, rank+2, ... (mod world) — the pairs of the reference's unidirectional ring
     (rwightman_sigmoid_loss.py:108-122 receives from the left neighbour, i.e. rank-1, rank-2, ...; the set of
-    (image-rank, text-chunk) pairs covered is identical, only the direction differs)."""
-    return [(rank + k) % world for k in range(world)]
+    (image-rank, text-chunk) pairs covered is identical, only the direction differs).
+    bidir=True: rank+1, rank-1, rank+2, rank-2, ... — the order of its bidirectional exchange (:75-107).
+    Either way every owner is read by exactly one rank at every step (mirrors step_owner() in csrc/siglip_capi.cu)."""
+    def offset(k):
+        if not bidir:
+            return k
+        return (k + 1) // 2 if (k & 1) else -(k // 2)
+    return [(rank + offset(k)) % world for k in range(world)]
 
 
 class SigmoidLossEngine:
@@ -311,9 +317,10 @@ class _SigmoidLossFn(torch.autograd.Function):
 
 
 class _EngineCache:
-    def __init__(self, group=None, cta_group: int = 2, overlap_pull: bool = True, sync_scalar_grads: bool = False):
+    def __init__(self, group=None, cta_group: int = 2, overlap_pull: bool = True, sync_scalar_grads: bool = False,
+                 bidir: bool = False):
         self.group, self.cta_group, self.overlap_pull = group, cta_group, overlap_pull
-        self.sync_scalar_grads = sync_scalar_grads
+        self.sync_scalar_grads, self.bidir = sync_scalar_grads, bidir
         self._engines: Dict[Tuple[int, int, int], SigmoidLossEngine] = {}
 
     def get(self, batch: int, dim: int, device: torch.device) -> SigmoidLossEngine:
@@ -324,6 +331,8 @@ class _EngineCache:
             eng = SigmoidLossEngine(batch, dim, dev, self.group, self.cta_group, self.overlap_pull)
             if self.sync_scalar_grads:
                 eng.set_option(_capi.SIGLIP_OPT_SYNC_SCALAR_GRADS, 1)
+            if self.bidir:
+                eng.set_option(_capi.SIGLIP_OPT_BIDIR, 1)
             self._engines[key] = eng
         return eng
 
@@ -384,8 +393,9 @@ SigmoidLoss = DDPSigmoidLoss
 
 class SigLipLoss(nn.Module):
     """open_clip-signature adapter (rwightman_sigmoid_loss.py:12-124): scale and bias are passed in, the ring
-    exchange of the original is replaced by the direct NVSwitch pulls of the fused path. ``bidir`` is accepted
-    for signature parity; the visiting order of chunks does not change the result."""
+    exchange of the original is replaced by the direct NVSwitch pulls of the fused path. ``bidir`` selects the
+    visiting order of the original's bidirectional exchange (rank+1, rank-1, rank+2, ...) instead of rank+1, rank+2,
+    ...; the pairs covered and the result are the same."""
 
     def __init__(self, cache_labels: bool = False, rank: int = 0, world_size: int = 1, bidir: bool = True,
                  use_horovod: bool = False, group=None, cta_group: int = 2):
@@ -393,7 +403,7 @@ class SigLipLoss(nn.Module):
         assert not use_horovod  # same restriction as the reference (rwightman_sigmoid_loss.py:35)
         self.cache_labels, self.rank, self.world_size, self.bidir = cache_labels, rank, world_size, bidir
         self.use_horovod = use_horovod
-        self._cache = _EngineCache(group, cta_group)
+        self._cache = _EngineCache(group, cta_group, bidir=bidir)
 
     def forward(self, image_features, text_features, logit_scale, logit_bias, output_dict: bool = False):
         _validate(image_features, text_features, None)

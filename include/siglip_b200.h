@@ -47,6 +47,9 @@ enum {
                                         all-reduce of the two parameters does, README.md:20,
                                         test_distributed_sigmoid_loss.py:79-83), exchanged through peer memory by a
                                         one-warp kernel; bit-identical on every rank. Collective: set on all ranks */
+  SIGLIP_OPT_BIDIR = 12, /* 1: visit the text chunks in the order r, r+1, r-1, r+2, r-2, ... (the order of the reference's
+                            bidirectional exchange, rwightman_sigmoid_loss.py:75-107) instead of r, r+1, r+2, ...;
+                            same pairs, same result up to fp32 summation order. Collective: set on all ranks */
   SIGLIP_OPT_GRAD_BF16 = 7     /* 1: siglip_fwd_bwd writes dimg / dtxt as bf16 [B, D] (the dtype autograd returns for bf16 inputs); default 0 = fp32 */
 };
 

@@ -93,15 +93,19 @@ def test_siglip_adapter_signature():
         SigLipLoss(use_horovod=True)
 
 
+@pytest.mark.parametrize("bidir", [False, True])
 @pytest.mark.parametrize("world", [1, 2, 3, 4, 5, 8])
-def test_chunk_schedule_covers_every_pair_once(world):
+def test_chunk_schedule_covers_every_pair_once(world, bidir):
     """Every (image rank, text chunk) pair is scored exactly once; step 0 is the own chunk (positives); at every
-    step the W ranks read W distinct owners (a permutation: no NVSwitch hot spot)."""
+    step the W ranks read W distinct owners (a permutation: no NVSwitch hot spot). bidir = the visiting order of the
+    reference's bidirectional exchange (rwightman_sigmoid_loss.py:75-107): right, left, right+1, left+1, ..."""
     seen = set()
     for r in range(world):
-        sched = chunk_schedule(r, world)
+        sched = chunk_schedule(r, world, bidir)
         assert sched[0] == r and sorted(sched) == list(range(world))
         seen.update((r, c) for c in sched)
     assert len(seen) == world * world
     for k in range(world):
-        assert sorted(chunk_schedule(r, world)[k] for r in range(world)) == list(range(world))
+        assert sorted(chunk_schedule(r, world, bidir)[k] for r in range(world)) == list(range(world))
+    if bidir and world >= 3:
+        assert chunk_schedule(0, world, True)[1:3] == [1, world - 1]

@@ -48,7 +48,7 @@ def _worker(rank, world, port, case_name, ret):
         gathered = [torch.empty_like(txt) for _ in range(world)]
         dist.all_gather(gathered, txt.detach())
     slots = [None] * world
-    for owner in chunk_schedule(rank, world):
+    for owner in chunk_schedule(rank, world, bidir=(world > 2)):   # either visiting order covers the same pairs
         a = img.detach().clone().requires_grad_(True)
         t = gathered[owner].clone().requires_grad_(True)
         tp2 = torch.tensor(c["t_prime"], dtype=torch.float64)
@@ -60,6 +60,16 @@ def _worker(rank, world, port, case_name, ret):
     everyone = [torch.empty_like(mine) for _ in range(world)]
     dist.all_gather(everyone, mine)                 # (gloo has no all_to_all; owners pick their slot of each rank)
     out["dtxt_slots"] = torch.stack([e[rank] for e in everyone]).sum(0).numpy()
+
+    # (2b) SIGLIP_OPT_SYNC_SCALAR_GRADS semantics: mean over ranks of (dt', dbias), rank-ordered sum (bit-identical
+    # on every rank) — what average_gradients does for the two parameters (test_distributed_sigmoid_loss.py:79-83)
+    pair = torch.tensor([out["dt_prime"], out["dbias"]], dtype=torch.float32)
+    pairs = [torch.empty_like(pair) for _ in range(world)]
+    dist.all_gather(pairs, pair)
+    acc = torch.zeros(2)
+    for p_ in pairs:
+        acc = acc + p_
+    out["scalar_mean"] = (acc / world).numpy()
 
     # (3) handle bootstrap
     blob = bytes([rank]) * 208
@@ -88,3 +98,7 @@ def test_multi_rank_host_logic_over_gloo(case_name, port):
         np.testing.assert_allclose(out["dtxt_slots"], ref["dtxt"], rtol=1e-4, atol=1e-6)
         assert abs(out["dt_prime"] - float(ref["dt_prime"])) <= 1e-5 * abs(float(ref["dt_prime"])) + 1e-7
         assert abs(out["dbias"] - float(ref["dbias"])) <= 1e-5 * abs(float(ref["dbias"])) + 1e-7
+        want = np.mean([[float(c["variants"]["ddp"][q]["dt_prime"]), float(c["variants"]["ddp"][q]["dbias"])]
+                        for q in range(world)], axis=0)
+        np.testing.assert_allclose(out["scalar_mean"], want, rtol=1e-5)
+        np.testing.assert_array_equal(out["scalar_mean"], ret[0]["scalar_mean"])

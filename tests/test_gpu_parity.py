@@ -508,3 +508,35 @@ def test_scalar_gradient_mean_option_loopback():
         assert abs(float(dtp1) - float(dtp0)) <= 1e-6 * abs(float(dtp0))
         assert abs(float(db1) - float(db0)) <= 1e-6 * abs(float(db0))
     eng.close()
+
+
+@pytest.mark.parametrize("name", ["w4_b8_d64", "w5_b4_d32"])
+def test_bidirectional_order_matches_reference_fixture(name):
+    """SIGLIP_OPT_BIDIR (chunks visited right, left, right+1, ... like rwightman_sigmoid_loss.py:75-107): same pairs,
+    so the loopback replay of every rank must reproduce the reference's bidirectional-variant outputs."""
+    from distributed_sigmoid_loss_b200 import _capi
+    if name not in golden_cases():
+        pytest.skip("fixture not present")
+    c = load_golden(name)
+    W, B, D = c["world"], c["batch"], c["dim"]
+    variant = "rw_bidir" if "rw_bidir" in c["variants"] else "ddp"
+    dtxt_sum = [torch.zeros(B, D, device=_dev()) for _ in range(W)]
+    for r in range(W):
+        eng = _engine(B, D, 2, rank_world=(r, W), loopback=True)
+        eng.set_option(_capi.SIGLIP_OPT_BIDIR, 1)
+        for k in range(W):
+            eng.debug_set_text_chunk(k, _golden_rank_inputs(c, k)[1])
+        img, txt = _golden_rank_inputs(c, r)
+        loss, dimg, _, dtp, db = eng.fwd_bwd(img, txt, _scal(c["t_prime"]), _scal(c["bias"]))
+        torch.cuda.synchronize()
+        ref = c["variants"][variant][r]
+        _check(f"loss r{r}", loss, ref["loss"])
+        _check(f"dimg r{r}", dimg, ref["dimg"])
+        _check(f"dt_prime r{r}", dtp, ref["dt_prime"])
+        _check(f"dbias r{r}", db, ref["dbias"])
+        for k in range(W):
+            dtxt_sum[k] += eng.debug_get_slot(k)
+        torch.cuda.synchronize()
+        eng.close()
+    for k in range(W):
+        _check(f"dtxt owner {k}", dtxt_sum[k], c["variants"][variant][k]["dtxt"])

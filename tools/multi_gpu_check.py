@@ -130,6 +130,18 @@ def main() -> int:
             not_bit_identical=0.0 if identical else 1.0), tol=1e-5)
     eng.set_option(_capi.SIGLIP_OPT_SYNC_SCALAR_GRADS, 0)
 
+    # ---- bidirectional visiting order (same pairs, other order) against the same fp32 autograd ----
+    eng.set_option(_capi.SIGLIP_OPT_BIDIR, 1)
+    for rep in range(2):
+        loss, dimg, dtxt, dtp, db = eng.fwd_bwd(img, txt, torch.tensor([tp], device=dev), torch.tensor([bias], device=dev))
+        torch.cuda.synchronize()
+        report(f"bidir order rep{rep} B={B} D={D}", dict(
+            loss=abs(float(loss) - ref["loss"]) / abs(ref["loss"]),
+            dimg=rel_f(dimg, ref["dimg"]), dtxt=rel_f(dtxt, contrib[rank]),
+            dtp=abs(float(dtp) - ref["dt_prime"]) / abs(ref["dt_prime"]),
+            db=abs(float(db) - ref["dbias"]) / abs(ref["dbias"])))
+    eng.set_option(_capi.SIGLIP_OPT_BIDIR, 0)
+
     # ---- timing at the headline per-rank shape -------------------------------------------------------------
     if args.time:
         B, D = args.batch, args.dim
