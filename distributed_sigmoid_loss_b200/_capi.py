@@ -32,6 +32,8 @@ EXPORTED_SYMBOLS = (
     "siglip_fwd_bwd",
     "siglip_fwd",
     "siglip_fwd_bwd_host",
+    "siglip_host_submit",
+    "siglip_host_wait",
     "siglip_scale",
     "siglip_normalize_fwd",
     "siglip_normalize_bwd",
@@ -123,6 +125,11 @@ def lib() -> ctypes.CDLL:
     L.siglip_fwd.restype = ci
     L.siglip_fwd_bwd_host.argtypes = [vp, vp, vp, ctypes.c_float, ctypes.c_float, vp, vp, vp, vp, vp, vp]
     L.siglip_fwd_bwd_host.restype = ci
+    L.siglip_host_submit.argtypes = [vp, vp, vp, ctypes.c_float, ctypes.c_float,
+                                     ctypes.POINTER(ctypes.c_ulonglong), vp]
+    L.siglip_host_submit.restype = ci
+    L.siglip_host_wait.argtypes = [vp, ctypes.c_ulonglong, vp, vp, vp]
+    L.siglip_host_wait.restype = ci
     L.siglip_normalize_fwd.argtypes = [vp, vp, ci, vp, vp, vp]
     L.siglip_normalize_fwd.restype = ci
     L.siglip_normalize_bwd.argtypes = [vp, vp, ci, vp, vp, ci, vp, vp]

@@ -173,10 +173,14 @@ struct siglip_ctx {
   std::vector<cudaEvent_t> ev_loss, ev_grad;  // start, stop, start, stop, ...
   size_t ev_loss_used = 0, ev_grad_used = 0;
   // host-API staging
-  __nv_bfloat16* h_img = nullptr;
-  __nv_bfloat16* h_txt = nullptr;
+  __nv_bfloat16* h_img[2] = {nullptr, nullptr};   // device staging of the host entries, two sets (pipelining)
+  __nv_bfloat16* h_txt[2] = {nullptr, nullptr};
   float* h_dimg = nullptr;
   float* h_dtxt = nullptr;
+  float* h_pinned = nullptr;                       // pinned host: [2][8] = {t', bias, -, -, loss, dt', dbias, -} per set
+  cudaStream_t copy_stream = nullptr;
+  cudaEvent_t ev_h2d[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
+  unsigned long long host_submitted = 0;           // tickets handed out so far
 };
 
 namespace {
@@ -784,40 +788,97 @@ int siglip_fwd(siglip_ctx* c, const void* img, const void* txt, const float* t_p
   return siglip_forward(c, img, txt, t_prime, bias, loss, 0, cuda_stream);
 }
 
-int siglip_fwd_bwd_host(siglip_ctx* c, const void* img_host, const void* txt_host, float t_prime, float bias,
-                        float* loss_host, float* dimg_host, float* dtxt_host, float* dt_prime_host,
-                        float* dbias_host, void* cuda_stream) {
-  if (c == nullptr || img_host == nullptr || txt_host == nullptr || loss_host == nullptr)
+// device scalars of host-entry set s: t', bias, loss, dt', dbias
+static inline float* host_set_scalars(siglip_ctx* c, int s) { return c->scalars + (s ? 10 : 0); }
+
+static int host_entry_init(siglip_ctx* c) {
+  if (c->h_img[0] != nullptr) return 0;
+  const size_t chunk_elems = static_cast<size_t>(c->B) * c->D;
+  for (int s = 0; s < 2; ++s) {
+    CK(cudaMalloc(reinterpret_cast<void**>(&c->h_img[s]), chunk_elems * sizeof(__nv_bfloat16)));
+    CK(cudaMalloc(reinterpret_cast<void**>(&c->h_txt[s]), chunk_elems * sizeof(__nv_bfloat16)));
+    CK(cudaEventCreateWithFlags(&c->ev_h2d[s], cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&c->ev_done[s], cudaEventDisableTiming));
+  }
+  CK(cudaMalloc(reinterpret_cast<void**>(&c->h_dimg), chunk_elems * sizeof(float)));
+  CK(cudaMalloc(reinterpret_cast<void**>(&c->h_dtxt), chunk_elems * sizeof(float)));
+  CK(cudaHostAlloc(reinterpret_cast<void**>(&c->h_pinned), 16 * sizeof(float), cudaHostAllocDefault));
+  CK(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+  c->workspace_bytes += chunk_elems * (4 * sizeof(__nv_bfloat16) + 2 * sizeof(float));
+  return 0;
+}
+
+// Enqueue one end-to-end step: the host->device copies of ITS inputs go to an internal copy stream into staging set
+// (ticket & 1), the step runs on the caller's stream once they have landed, its (loss, dt', dbias) are copied to pinned
+// host memory behind it. With two staging sets the copies of step n+1 overlap the kernels of step n.
+int siglip_host_submit(siglip_ctx* c, const void* img_host, const void* txt_host, float t_prime, float bias,
+                       unsigned long long* ticket, void* cuda_stream) {
+  if (c == nullptr || img_host == nullptr || txt_host == nullptr || ticket == nullptr)
     return fail(SIGLIP_ERR_INVALID, "null argument");
   cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
   CK(cudaSetDevice(c->device));
-  const size_t chunk_elems = static_cast<size_t>(c->B) * c->D;
-  if (c->h_img == nullptr) {
-    CK(cudaMalloc(reinterpret_cast<void**>(&c->h_img), chunk_elems * sizeof(__nv_bfloat16)));
-    CK(cudaMalloc(reinterpret_cast<void**>(&c->h_txt), chunk_elems * sizeof(__nv_bfloat16)));
-    CK(cudaMalloc(reinterpret_cast<void**>(&c->h_dimg), chunk_elems * sizeof(float)));
-    CK(cudaMalloc(reinterpret_cast<void**>(&c->h_dtxt), chunk_elems * sizeof(float)));
-    c->workspace_bytes += chunk_elems * (2 * sizeof(__nv_bfloat16) + 2 * sizeof(float));
+  int rc;
+  if ((rc = host_entry_init(c))) return rc;
+  const size_t chunk_bytes = static_cast<size_t>(c->B) * c->D * sizeof(__nv_bfloat16);
+  const unsigned long long n = c->host_submitted;
+  const int s = static_cast<int>(n & 1);
+  if (n >= 2) {
+    // set s was used by step n-2: its kernels must be done before the staging buffers are overwritten, and the
+    // caller must have collected its results (siglip_host_wait) before the pinned slot is reused
+    CK(cudaStreamWaitEvent(c->copy_stream, c->ev_done[s], 0));
+    CK(cudaEventSynchronize(c->ev_done[s]));
   }
-  const float sc[2] = {t_prime, bias};
-  CK(cudaMemcpyAsync(c->scalars, sc, sizeof(sc), cudaMemcpyHostToDevice, st));
-  CK(cudaMemcpyAsync(c->h_img, img_host, chunk_elems * sizeof(__nv_bfloat16), cudaMemcpyHostToDevice, st));
-  CK(cudaMemcpyAsync(c->h_txt, txt_host, chunk_elems * sizeof(__nv_bfloat16), cudaMemcpyHostToDevice, st));
+  float* pin = c->h_pinned + 8 * s;
+  pin[0] = t_prime;
+  pin[1] = bias;
+  float* sc = host_set_scalars(c, s);
+  CK(cudaMemcpyAsync(sc, pin, 2 * sizeof(float), cudaMemcpyHostToDevice, c->copy_stream));
+  CK(cudaMemcpyAsync(c->h_img[s], img_host, chunk_bytes, cudaMemcpyHostToDevice, c->copy_stream));
+  CK(cudaMemcpyAsync(c->h_txt[s], txt_host, chunk_bytes, cudaMemcpyHostToDevice, c->copy_stream));
+  CK(cudaEventRecord(c->ev_h2d[s], c->copy_stream));
+  CK(cudaStreamWaitEvent(st, c->ev_h2d[s], 0));
   const int saved_bf16 = c->grad_bf16;
-  c->grad_bf16 = 0;  // the host entry returns fp32 gradients
-  int rc = siglip_fwd_bwd(c, c->h_img, c->h_txt, c->scalars + 0, c->scalars + 1, c->scalars + 2, c->h_dimg, c->h_dtxt,
-                          c->scalars + 3, c->scalars + 4, st);
+  c->grad_bf16 = 0;  // the host entries produce fp32 gradients
+  rc = siglip_fwd_bwd(c, c->h_img[s], c->h_txt[s], sc + 0, sc + 1, sc + 2, c->h_dimg, c->h_dtxt, sc + 3, sc + 4, st);
   c->grad_bf16 = saved_bf16;
   if (rc) return rc;
-  float res[3];
-  CK(cudaMemcpyAsync(res, c->scalars + 2, sizeof(res), cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(pin + 4, sc + 2, 3 * sizeof(float), cudaMemcpyDeviceToHost, st));
+  CK(cudaEventRecord(c->ev_done[s], st));
+  c->host_submitted = n + 1;
+  *ticket = n;
+  return 0;
+}
+
+int siglip_host_wait(siglip_ctx* c, unsigned long long ticket, float* loss_host, float* dt_prime_host,
+                     float* dbias_host) {
+  if (c == nullptr || loss_host == nullptr) return fail(SIGLIP_ERR_INVALID, "null argument");
+  if (ticket >= c->host_submitted || ticket + 2 < c->host_submitted)
+    return fail(SIGLIP_ERR_STATE, "ticket is not one of the last two submitted steps");
+  CK(cudaSetDevice(c->device));
+  const int s = static_cast<int>(ticket & 1);
+  CK(cudaEventSynchronize(c->ev_done[s]));
+  int rc;
+  if ((rc = check_dbg(c, "siglip_host_wait"))) return rc;
+  const float* pin = c->h_pinned + 8 * s;
+  *loss_host = pin[4];
+  if (dt_prime_host) *dt_prime_host = pin[5];
+  if (dbias_host) *dbias_host = pin[6];
+  return 0;
+}
+
+int siglip_fwd_bwd_host(siglip_ctx* c, const void* img_host, const void* txt_host, float t_prime, float bias,
+                        float* loss_host, float* dimg_host, float* dtxt_host, float* dt_prime_host,
+                        float* dbias_host, void* cuda_stream) {
+  if (loss_host == nullptr) return fail(SIGLIP_ERR_INVALID, "null argument");
+  unsigned long long ticket = 0;
+  int rc = siglip_host_submit(c, img_host, txt_host, t_prime, bias, &ticket, cuda_stream);
+  if (rc) return rc;
+  cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+  const size_t chunk_elems = static_cast<size_t>(c->B) * c->D;
   if (dimg_host) CK(cudaMemcpyAsync(dimg_host, c->h_dimg, chunk_elems * sizeof(float), cudaMemcpyDeviceToHost, st));
   if (dtxt_host) CK(cudaMemcpyAsync(dtxt_host, c->h_dtxt, chunk_elems * sizeof(float), cudaMemcpyDeviceToHost, st));
-  CK(cudaStreamSynchronize(st));
-  if ((rc = check_dbg(c, "siglip_fwd_bwd_host"))) return rc;
-  *loss_host = res[0];
-  if (dt_prime_host) *dt_prime_host = res[1];
-  if (dbias_host) *dbias_host = res[2];
+  if ((rc = siglip_host_wait(c, ticket, loss_host, dt_prime_host, dbias_host))) return rc;
+  if (dimg_host || dtxt_host) CK(cudaStreamSynchronize(st));
   return 0;
 }
 
@@ -1079,8 +1140,14 @@ void siglip_ctx_destroy(siglip_ctx* c) {
   cudaFree(c->reduce_ptrs_dev);
   cudaFree(c->signal_ptrs_dev);
   cudaFree(c->mailbox_ptrs_dev);
-  cudaFree(c->h_img);
-  cudaFree(c->h_txt);
+  for (int s = 0; s < 2; ++s) {
+    cudaFree(c->h_img[s]);
+    cudaFree(c->h_txt[s]);
+    if (c->ev_h2d[s]) cudaEventDestroy(c->ev_h2d[s]);
+    if (c->ev_done[s]) cudaEventDestroy(c->ev_done[s]);
+  }
+  if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
+  if (c->h_pinned) cudaFreeHost(c->h_pinned);
   cudaFree(c->h_dimg);
   cudaFree(c->h_dtxt);
   if (c->dbg_host) cudaFreeHost(c->dbg_host);

@@ -212,10 +212,7 @@ class SigmoidLossEngine:
                      dimg_host: Optional[torch.Tensor] = None, dtxt_host: Optional[torch.Tensor] = None):
         """End-to-end step on HOST bf16 buffers (pinned recommended): H2D, step, D2H inside one C call.
         Returns (loss, dt_prime, dbias) as Python floats."""
-        for x in (img_host, txt_host):
-            if x.device.type != "cpu" or x.dtype != torch.bfloat16 or not x.is_contiguous() or \
-                    tuple(x.shape) != (self.batch, self.dim):
-                raise RuntimeError("fwd_bwd_host expects contiguous CPU bf16 tensors of shape [B, D]")
+        self._check_host(img_host, txt_host)
         out = (ctypes.c_float * 3)()
         loss_p = ctypes.cast(out, ctypes.c_void_p).value
         with torch.cuda.device(self.device):
@@ -225,6 +222,30 @@ class SigmoidLossEngine:
                 dtxt_host.data_ptr() if dtxt_host is not None else None,
                 loss_p + 4, loss_p + 8, self._stream()))
         return float(out[0]), float(out[1]), float(out[2])
+
+    def host_submit(self, img_host: torch.Tensor, txt_host: torch.Tensor, t_prime: float, bias: float) -> int:
+        """Pipelined end-to-end step on HOST bf16 buffers: enqueue this step's host->device copies (internal copy
+        stream, two staging sets), the step and the device->host copy of its scalars; returns a ticket for
+        ``host_wait``. At most two steps in flight; the host tensors must stay alive until the ticket is waited."""
+        self._check_host(img_host, txt_host)
+        ticket = ctypes.c_ulonglong(0)
+        with torch.cuda.device(self.device):
+            _capi.check(self._L.siglip_host_submit(self._h, img_host.data_ptr(), txt_host.data_ptr(), float(t_prime),
+                                                   float(bias), ctypes.byref(ticket), self._stream()))
+        return int(ticket.value)
+
+    def host_wait(self, ticket: int):
+        """(loss, dt_prime, dbias) of a submitted step, as Python floats, once they are on the host."""
+        out = (ctypes.c_float * 3)()
+        p = ctypes.cast(out, ctypes.c_void_p).value
+        _capi.check(self._L.siglip_host_wait(self._h, ticket, p, p + 4, p + 8))
+        return float(out[0]), float(out[1]), float(out[2])
+
+    def _check_host(self, img_host: torch.Tensor, txt_host: torch.Tensor) -> None:
+        for x in (img_host, txt_host):
+            if x.device.type != "cpu" or x.dtype != torch.bfloat16 or not x.is_contiguous() or \
+                    tuple(x.shape) != (self.batch, self.dim):
+                raise RuntimeError("the host entries expect contiguous CPU bf16 tensors of shape [B, D]")
 
     def _check(self, img: torch.Tensor, txt: torch.Tensor) -> None:
         for x in (img, txt):

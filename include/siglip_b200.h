@@ -143,8 +143,20 @@ int siglip_fwd(siglip_ctx* ctx, const void* img, const void* txt, const float* t
 /*
  * Same step with HOST buffers (pinned or pageable): host->device copies of img/txt, the step, and
  * device->host copies of loss (+ gradients when the pointers are non-null) all inside the call, which returns
- * after the stream has drained. This is the end-to-end entry the benchmark times.
+ * after the step has finished (= siglip_host_submit + siglip_host_wait). fp32 gradients stay in device staging
+ * unless dimg_host / dtxt_host are given.
+ *
+ * siglip_host_submit / siglip_host_wait: the same end-to-end step, pipelined. submit enqueues the host->device copies
+ * of THIS step's inputs on an internal copy stream (two staging sets), the step on cuda_stream behind them and the
+ * device->host copy of (loss, dt_prime, dbias) behind that, and returns a ticket; wait blocks until that step's
+ * results are on the host. At most two steps may be in flight: submit blocks on the step that used the same staging
+ * set. The copies of step n+1 overlap the kernels of step n; every step still pays its own copies.
+ * This is the end-to-end entry the benchmark times. Host buffers must stay valid until the step's wait returns.
  */
+int siglip_host_submit(siglip_ctx* ctx, const void* img_host, const void* txt_host, float t_prime, float bias,
+                       unsigned long long* ticket, void* cuda_stream);
+int siglip_host_wait(siglip_ctx* ctx, unsigned long long ticket, float* loss_host, float* dt_prime_host,
+                     float* dbias_host);
 int siglip_fwd_bwd_host(siglip_ctx* ctx, const void* img_host, const void* txt_host, float t_prime, float bias,
                         float* loss_host, float* dimg_host, float* dtxt_host, float* dt_prime_host,
                         float* dbias_host, void* cuda_stream);
