@@ -142,6 +142,8 @@ struct siglip_ctx {
   int epi_sleep_loss_ns = 0;
   int sync_scalar_grads = 0;             // backward returns the mean over ranks of dt' / dbias
   int bidir = 0;                         // visiting order of the text chunks: r, r+1, r-1, r+2, r-2, ...
+  // diagnostics, read from the environment once at context creation (see include/siglip_b200.h)
+  bool dbg_no_gstore = false, dbg_no_cvt = false, dbg_loss_waitstats = false;
   // workspaces
   __nv_bfloat16* txt_all = nullptr;      // [world][B, D] bf16; slot `rank` is what the peers pull (world > 1)
   __nv_bfloat16* G[kMaxWorld] = {};      // per step k: [Bp, Bp] sigma operand (fp16 bits x kGScale), diagonal zeroed
@@ -270,8 +272,8 @@ int run_loss_chunk(siglip_ctx* c, int k, const void* img, const __nv_bfloat16* t
   p.pull_wait_flag = pull.flag;
   p.pull_wait_value = pull.value;
   p.epi_sleep_ns = static_cast<unsigned int>(c->epi_sleep_loss_ns);
-  if (save && getenv("SIGLIP_DEBUG_NO_GSTORE")) p.store_g = 0;  // timing experiments only (wrong gradients)
-  if (save && !getenv("SIGLIP_DEBUG_NO_CVT")) {
+  if (save && c->dbg_no_gstore) p.store_g = 0;  // timing experiments only (wrong gradients)
+  if (save && !c->dbg_no_cvt) {
     const size_t chunk_elems = static_cast<size_t>(c->B) * c->D;
     const unsigned long long n16 = chunk_elems * sizeof(__nv_bfloat16) / 16;
     p.cvt_scale = kXScale;
@@ -285,7 +287,7 @@ int run_loss_chunk(siglip_ctx* c, int k, const void* img, const __nv_bfloat16* t
     }
   }
   unsigned long long* wstats = nullptr;
-  if (getenv("SIGLIP_DEBUG_LOSS_WAITSTATS")) {   // diagnostic: where the roles of the loss kernel spend their cycles
+  if (c->dbg_loss_waitstats) {   // diagnostic: where the roles of the loss kernel spend their cycles
     CK(cudaMalloc(reinterpret_cast<void**>(&wstats), 8 * 256 * sizeof(unsigned long long)));
     CK(cudaMemsetAsync(wstats, 0, 8 * 256 * sizeof(unsigned long long), st));
     p.wait_stats = wstats;
@@ -607,6 +609,9 @@ int siglip_ctx_create(siglip_ctx** out, int device, int rank, int world, int B, 
   c->B = B;
   c->D = D;
   c->Bp = round_up(B, 256);
+  c->dbg_no_gstore = getenv("SIGLIP_DEBUG_NO_GSTORE") != nullptr;
+  c->dbg_no_cvt = getenv("SIGLIP_DEBUG_NO_CVT") != nullptr;
+  c->dbg_loss_waitstats = getenv("SIGLIP_DEBUG_LOSS_WAITSTATS") != nullptr;
   CK(cudaDeviceGetAttribute(&c->num_sms, cudaDevAttrMultiProcessorCount, device));
   const size_t chunk_elems = static_cast<size_t>(B) * D;
   size_t total = 0;

@@ -32,6 +32,15 @@ enum {
   SIGLIP_ERR_STATE = 4      /* call sequence error (e.g. world > 1 without imported peer handles) */
 };
 
+/*
+ * Diagnostics read from the environment (never needed in production):
+ *   SIGLIP_DEBUG_LOSS_WAITSTATS  print per-role wait / loop cycle counts of every loss-kernel launch (synchronises)
+ *   SIGLIP_DEBUG_NO_GSTORE, SIGLIP_DEBUG_NO_CVT   timing experiments: skip the sigma store / the fp16 operand copies
+ *                                (the gradients are then WRONG)
+ *   SIGLIP_DEBUG_PRINT_TIMES     print the per-launch CUDA-event times collected under SIGLIP_OPT_KERNEL_TIMING
+ *   SIGLIP_DEBUG_MCAST, _AB_F16, _WAITSTATS, _EPI_SLEEP, _STAGES   variants of siglip_debug_gemm(_timed) only
+ */
+
 /* tuning knobs (siglip_ctx_set_option) */
 enum {
   SIGLIP_OPT_CTA_GROUP = 1, /* 1: cta_group::1 128x256 tiles; 2: cta_group::2 256x256 tiles per SM pair (default) */
