@@ -231,6 +231,10 @@ def run_reference(args):
         sys.stdout.write(out.stdout)
         sys.stdout.flush()
         return out.returncode
+    try:     # a parent bench process may have pinned itself to the GPU's NUMA node: the CPU arm uses every host core
+        os.sched_setaffinity(0, range(os.cpu_count() or 1))
+    except OSError:
+        pass
     import torch
 
     B, D, W = args.batch, args.dim, args.gpus
