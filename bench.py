@@ -341,9 +341,11 @@ def run_ours(args):
     eng.set_option(_capi.SIGLIP_OPT_KERNEL_TIMING, 1)
     launches0 = eng.launch_count
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    # NVML queries take milliseconds: read the NVLink counters OUTSIDE the barrier-bracketed timed region (a late rank 0
+    # would make every peer wait for its flags inside their kernels)
+    nvl0 = _nvlink_counters(local_rank) if (rank == 0 and world > 1) else None
     barrier()
     first_sample = sampler.mark()
-    nvl0 = _nvlink_counters(local_rank) if (rank == 0 and world > 1) else None
     e0.record()
     for _ in range(args.steps):
         loss = step()
