@@ -165,6 +165,42 @@ __device__ __forceinline__ void tma_load_2d(const CUtensorMap* m, uint32_t bar, 
   }
 }
 
+// L2 eviction-priority policies for streamed vs re-used operands (createpolicy; whole line range, fraction 1.0).
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_normal() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+
+// tma_load_2d with an L2 cache policy for the lines it touches.
+template <int kCG>
+__device__ __forceinline__ void tma_load_2d_hint(const CUtensorMap* m, uint32_t bar, uint32_t dst, int c0, int c1,
+                                                 uint64_t policy) {
+  if constexpr (kCG == 1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
+        " [%0], [%1, {%3, %4}], [%2], %5;" ::"r"(dst),
+        "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1), "l"(policy)
+        : "memory");
+  } else {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
+        " [%0], [%1, {%3, %4}], [%2], %5;" ::"r"(dst),
+        "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1), "l"(policy)
+        : "memory");
+  }
+}
+
 // Same load, delivered to the same shared-memory offset of every CTA in `cta_mask` of the cluster; each
 // destination CTA's barrier at offset `bar` receives the complete_tx. One L2 read feeds all destinations.
 __device__ __forceinline__ void tma_load_2d_mcast(const CUtensorMap* m, uint32_t bar, uint32_t dst, int c0, int c1,

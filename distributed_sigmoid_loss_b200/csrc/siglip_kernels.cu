@@ -205,6 +205,7 @@ struct GStore {
   uint32_t stage;           // this warp's 2 KiB staging buffer (shared::cta address, 512-byte aligned)
   int row0;                 // first row of this warp's 32-row block
   int lane;
+  uint64_t policy;          // L2 evict_first: the sigma lines are not read again before they have left the L2
 };
 
 __device__ __forceinline__ void store_g_slab(const GStore& gs, int col0, const uint32_t (&packed)[16]) {
@@ -222,9 +223,9 @@ __device__ __forceinline__ void store_g_slab(const GStore& gs, int col0, const u
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the TMA engine
   __syncwarp();
   if (gs.lane == 0) {
-    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group.L2::cache_hint [%0, {%2, %3}], [%1], %4;" ::"l"(
                      reinterpret_cast<uint64_t>(gs.tmap)),
-                 "r"(gs.stage), "r"(col0), "r"(gs.row0)
+                 "r"(gs.stage), "r"(col0), "r"(gs.row0), "l"(gs.policy)
                  : "memory");
     asm volatile("cp.async.bulk.commit_group;" ::: "memory");
   }
@@ -444,6 +445,13 @@ siglip_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_consta
       int stage = 0;
       uint32_t phase = 0;
       long long w_empty = 0;
+      // L2 priorities: the embeddings (A and B of the loss kernel, B of the gradient kernel: 32 MiB each) are re-read
+      // by every tile wave and must survive the 512 MiB sigma operand streaming through the 126 MB L2 once per pass.
+      // The sigma operand itself keeps normal priority: the four column tiles of a row panel (and both CTAs of a pair)
+      // read the same lines a little apart in time and rely on finding them in L2 (evict_first there: 2.6 GB of DRAM
+      // reads per launch instead of 1.5).
+      const uint64_t pol_b = l2_policy_evict_last();
+      const uint64_t pol_a = (kMode == kModeLoss) ? pol_b : l2_policy_evict_normal();
       for (int t = cluster_id; t < total_tiles; t += num_clusters) {
         const TileCoord tc = decode_tile<kMC>(p, t, mc_rank);
         const Problem& pr = p.prob[tc.prob];
@@ -469,19 +477,19 @@ siglip_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_consta
             if constexpr (kCG == 2) fb = mapa_shared(fb, leader_rank);   // the pair's leader owns the full barriers
             const int k_idx = kb * kBlockK;
             if (!a_mn) {
-              tma_load_2d<kCG>(tmA, fb, sA, k_idx, m_idx);  // box {64 k, 128 rows}
+              tma_load_2d_hint<kCG>(tmA, fb, sA, k_idx, m_idx, pol_a);  // box {64 k, 128 rows}
             } else {
 #pragma unroll
               for (int h = 0; h < kBlockM / 64; ++h)        // boxes {64 rows, 64 k}
-                tma_load_2d<kCG>(tmA, fb, sA + h * 8192, m_idx + 64 * h, k_idx);
+                tma_load_2d_hint<kCG>(tmA, fb, sA + h * 8192, m_idx + 64 * h, k_idx, pol_a);
             }
             if constexpr (kMC == 1) {
               if (!b_mn) {
-                tma_load_2d<kCG>(tmB, fb, sB, k_idx, n_idx);  // box {64 k, kBRows rows}
+                tma_load_2d_hint<kCG>(tmB, fb, sB, k_idx, n_idx, pol_b);  // box {64 k, kBRows rows}
               } else {
 #pragma unroll
                 for (int h = 0; h < C::kBRows / 64; ++h)
-                  if (h * 64 < b_rows) tma_load_2d<kCG>(tmB, fb, sB + h * 8192, n_idx + 64 * h, k_idx);
+                  if (h * 64 < b_rows) tma_load_2d_hint<kCG>(tmB, fb, sB + h * 8192, n_idx + 64 * h, k_idx, pol_b);
               }
             } else if constexpr (kCG == 1) {
               // this CTA fetches 1/kMC of the common B tile and multicasts it to every CTA of the cluster
@@ -616,6 +624,7 @@ siglip_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_consta
     // was 11 % of the loss kernel's stall samples (the fp64 pipe of this part is narrow); fp64 only at the very end
     float s_sp = 0.f, s_g = 0.f, s_gs = 0.f, c_sp = 0.f, c_g = 0.f, c_gs = 0.f;
     long long w_epi = 0;
+    const uint64_t g_store_policy = l2_policy_evict_first();
     const long long epi_start = clock_cycles();
     int as = 0;
     uint32_t aphase = 0;
@@ -642,6 +651,7 @@ siglip_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_consta
       gst.stage = staging_base + static_cast<uint32_t>(warp) * kStagingBytesPerWarp;
       gst.row0 = tc.m_blk * C::kTileM + static_cast<int>(cta_rank) * kBlockM + q * 32;
       gst.lane = lane;
+      gst.policy = g_store_policy;
       float scale = 0.f, fix = 0.f;
       if constexpr (kMode == kModeLoss) {
         const int tile_m0 = tc.m_blk * C::kTileM, tile_n0 = tc.n_blk * kTileN;
