@@ -32,6 +32,7 @@ EXPORTED_SYMBOLS = (
     "siglip_fwd_bwd",
     "siglip_fwd",
     "siglip_fwd_bwd_host",
+    "siglip_convert_f32",
     "siglip_host_submit",
     "siglip_host_wait",
     "siglip_scale",
@@ -65,6 +66,7 @@ SIGLIP_OPT_EPI_SLEEP_GRAD_NS = 9
 SIGLIP_OPT_EPI_SLEEP_LOSS_NS = 10
 SIGLIP_OPT_SYNC_SCALAR_GRADS = 11
 SIGLIP_OPT_BIDIR = 12
+SIGLIP_OPT_INPUT_F16 = 13
 
 _lib: Optional[ctypes.CDLL] = None
 
@@ -125,6 +127,8 @@ def lib() -> ctypes.CDLL:
     L.siglip_fwd.restype = ci
     L.siglip_fwd_bwd_host.argtypes = [vp, vp, vp, ctypes.c_float, ctypes.c_float, vp, vp, vp, vp, vp, vp]
     L.siglip_fwd_bwd_host.restype = ci
+    L.siglip_convert_f32.argtypes = [vp, vp, vp, vp]
+    L.siglip_convert_f32.restype = ci
     L.siglip_host_submit.argtypes = [vp, vp, vp, ctypes.c_float, ctypes.c_float,
                                      ctypes.POINTER(ctypes.c_ulonglong), vp]
     L.siglip_host_submit.restype = ci

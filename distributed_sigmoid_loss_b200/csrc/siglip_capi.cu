@@ -142,6 +142,8 @@ struct siglip_ctx {
   int epi_sleep_loss_ns = 0;
   int sync_scalar_grads = 0;             // backward returns the mean over ranks of dt' / dbias
   int bidir = 0;                         // visiting order of the text chunks: r, r+1, r-1, r+2, r-2, ...
+  int input_f16 = 0;                     // img / txt are fp16(x * kXScale) instead of bf16 (fp32-input path)
+  int saved_f16 = 0;                     // format of the embeddings of the forward saved for backward
   // diagnostics, read from the environment once at context creation (see include/siglip_b200.h)
   bool dbg_no_gstore = false, dbg_no_cvt = false, dbg_loss_waitstats = false;
   // workspaces
@@ -249,6 +251,10 @@ int run_loss_chunk(siglip_ctx* c, int k, const void* img, const __nv_bfloat16* t
   KernelParams p;
   memset(&p, 0, sizeof(p));
   p.nprob = 1;
+  // fp32-input path: both operands are fp16(x * kXScale), the accumulator is kXScale^2 <img, txt>
+  p.prob[0].ab_f16 = c->input_f16;
+  p.s_scale = c->input_f16 ? 1.0f / (kXScale * kXScale) : 1.0f;
+  p.cvt_copy = c->input_f16;
   p.prob[0].M = c->B;
   p.prob[0].N = c->B;
   p.prob[0].K = c->D;
@@ -357,6 +363,8 @@ int run_grad_chunk(siglip_ctx* c, int k, const void* img, const __nv_bfloat16* t
     pr.ldo = c->D;
     pr.ldx = c->D;
     pr.fix_vec = own ? c->g_diag : nullptr;
+    pr.fix_f16 = c->saved_f16;
+    pr.fix_mat_scale = c->saved_f16 ? 1.0f / kXScale : 1.0f;
   }
   p.prob[0].a_mn = 0;
   p.prob[0].out = dimg_out;
@@ -480,6 +488,7 @@ int forward_impl(siglip_ctx* c, const void* img, const void* txt, const float* t
   }
   CK(cudaGetLastError());
   if (save) {
+    c->saved_f16 = c->input_f16;
     static unsigned long long next_gen = 0;
     c->gen = ++next_gen;
   }
@@ -681,6 +690,9 @@ int siglip_ctx_set_option(siglip_ctx* c, int option, int value) {
     case SIGLIP_OPT_EPI_SLEEP_LOSS_NS:
       c->epi_sleep_loss_ns = value < 0 ? 0 : value;
       return 0;
+    case SIGLIP_OPT_INPUT_F16:
+      c->input_f16 = value ? 1 : 0;
+      return 0;
     case SIGLIP_OPT_BIDIR:
       c->bidir = value ? 1 : 0;
       c->gen = 0;   // a saved forward was laid out in the other order
@@ -842,10 +854,12 @@ int siglip_host_submit(siglip_ctx* c, const void* img_host, const void* txt_host
   CK(cudaMemcpyAsync(c->h_txt[s], txt_host, chunk_bytes, cudaMemcpyHostToDevice, c->copy_stream));
   CK(cudaEventRecord(c->ev_h2d[s], c->copy_stream));
   CK(cudaStreamWaitEvent(st, c->ev_h2d[s], 0));
-  const int saved_bf16 = c->grad_bf16;
+  const int saved_bf16 = c->grad_bf16, saved_fmt = c->input_f16;
   c->grad_bf16 = 0;  // the host entries produce fp32 gradients
+  c->input_f16 = 0;  // ... from bf16 host buffers
   rc = siglip_fwd_bwd(c, c->h_img[s], c->h_txt[s], sc + 0, sc + 1, sc + 2, c->h_dimg, c->h_dtxt, sc + 3, sc + 4, st);
   c->grad_bf16 = saved_bf16;
+  c->input_f16 = saved_fmt;
   if (rc) return rc;
   CK(cudaMemcpyAsync(pin + 4, sc + 2, 3 * sizeof(float), cudaMemcpyDeviceToHost, st));
   CK(cudaEventRecord(c->ev_done[s], st));
@@ -969,7 +983,18 @@ int siglip_normalize_fwd(siglip_ctx* c, const void* x, int in_bf16, void* xhat_b
     return fail(SIGLIP_ERR_INVALID, "buffers must be 16-byte aligned");
   CK(cudaSetDevice(c->device));
   CKI(siglip::launch_normalize_fwd(x, in_bf16, static_cast<__nv_bfloat16*>(xhat_bf16), inv_norm, c->B, c->D,
-                                   c->num_sms, static_cast<cudaStream_t>(cuda_stream)));
+                                   c->input_f16 ? kXScale : 0.0f, c->num_sms, static_cast<cudaStream_t>(cuda_stream)));
+  c->launches++;
+  return 0;
+}
+
+int siglip_convert_f32(siglip_ctx* c, const float* x_f32, void* out_16bit, void* cuda_stream) {
+  if (c == nullptr || x_f32 == nullptr || out_16bit == nullptr) return fail(SIGLIP_ERR_INVALID, "null argument");
+  if ((reinterpret_cast<uintptr_t>(x_f32) & 15u) || (reinterpret_cast<uintptr_t>(out_16bit) & 15u))
+    return fail(SIGLIP_ERR_INVALID, "buffers must be 16-byte aligned");
+  CK(cudaSetDevice(c->device));
+  CKI(siglip::launch_convert_f32(x_f32, out_16bit, static_cast<size_t>(c->B) * c->D, c->input_f16 ? kXScale : 0.0f,
+                                 c->num_sms, static_cast<cudaStream_t>(cuda_stream)));
   c->launches++;
   return 0;
 }

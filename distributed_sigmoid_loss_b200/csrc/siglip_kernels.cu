@@ -328,6 +328,8 @@ __device__ __forceinline__ void out_slab(const uint32_t (&v)[32], float scale, i
                                          float fix) {
   if (row >= pr.M) return;
   const float as = pr.acc_scale;   // undoes the power-of-two scaling of the fp16 operands (1 for bf16)
+  const float xs = (pr.fix_mat_scale != 0.f) ? pr.fix_mat_scale : 1.0f;
+  const float fixs = fix * xs;
   const __nv_bfloat16* xrow = pr.fix_mat ? pr.fix_mat + static_cast<long long>(row) * pr.ldx : nullptr;
   const float* arow = pr.add_src ? pr.add_src + static_cast<long long>(row) * pr.ld_add : nullptr;
 #pragma unroll
@@ -342,8 +344,17 @@ __device__ __forceinline__ void out_slab(const uint32_t (&v)[32], float scale, i
         const uint32_t xw[4] = {xb.x, xb.y, xb.z, xb.w};
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
-          o[2 * e + 0] = fmaf(fix, __uint_as_float(xw[e] << 16), o[2 * e + 0]);
-          o[2 * e + 1] = fmaf(fix, __uint_as_float(xw[e] & 0xffff0000u), o[2 * e + 1]);
+          float x0, x1;
+          if (pr.fix_f16) {
+            const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&xw[e]));
+            x0 = f.x;
+            x1 = f.y;
+          } else {
+            x0 = __uint_as_float(xw[e] << 16);
+            x1 = __uint_as_float(xw[e] & 0xffff0000u);
+          }
+          o[2 * e + 0] = fmaf(fixs, x0, o[2 * e + 0]);
+          o[2 * e + 1] = fmaf(fixs, x1, o[2 * e + 1]);
         }
       }
 #pragma unroll
@@ -619,7 +630,10 @@ siglip_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_consta
     const int row_in_cta = q * 32 + lane;
     const float t_exact = expf(*p.t_prime);
     const float bias = (kMode == kModeLoss) ? *p.bias : 0.f;
-    const float tl = t_exact * kLog2e, bl = bias * kLog2e;
+    // loss kernel: z = t_eff * acc + b with t_eff = t * s_scale (the accumulator is 2^8 <img, txt> for fp16 x 16 operands)
+    const float s_scale = (kMode == kModeLoss && p.s_scale != 0.f) ? p.s_scale : 1.0f;
+    const float t_eff = t_exact * s_scale;
+    const float tl = t_eff * kLog2e, bl = bias * kLog2e;
     // per-thread running sums over the tiles of this CTA: compensated fp32 (Kahan) — a DADD per sum, thread and tile
     // was 11 % of the loss kernel's stall samples (the fp64 pipe of this part is narrow); fp64 only at the very end
     float s_sp = 0.f, s_g = 0.f, s_gs = 0.f, c_sp = 0.f, c_g = 0.f, c_gs = 0.f;
@@ -671,18 +685,18 @@ siglip_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_consta
             float smax = fmaxf(__uint_as_float(v[0]), __uint_as_float(v[1]));
 #pragma unroll
             for (int j = 2; j < 32; j += 2) smax = max3(smax, __uint_as_float(v[j]), __uint_as_float(v[j + 1]));
-            const bool fast = __all_sync(0xffffffffu, fmaf(smax, t_exact, bias) < kFastZ);
+            const bool fast = __all_sync(0xffffffffu, fmaf(smax, t_eff, bias) < kFastZ);
             if (fast)
               loss_slab_fast<true>(v, tl, bl, col0, sg, gst, p.g_scale, acc_sp, acc_g, acc_gs);
             else
-              loss_slab<false, false, true>(v, t_exact, bias, row, col0, pr.M, pr.N, sg, gst, p.g_scale, p.g_diag, acc_sp, acc_g, acc_gs);
+              loss_slab<false, false, true>(v, t_eff, bias, row, col0, pr.M, pr.N, sg, gst, p.g_scale, p.g_diag, acc_sp, acc_g, acc_gs);
           } else if (edge) {
             if (diag)
-              loss_slab<true, true, true>(v, t_exact, bias, row, col0, pr.M, pr.N, sg, gst, p.g_scale, p.g_diag, acc_sp, acc_g, acc_gs);
+              loss_slab<true, true, true>(v, t_eff, bias, row, col0, pr.M, pr.N, sg, gst, p.g_scale, p.g_diag, acc_sp, acc_g, acc_gs);
             else
-              loss_slab<true, false, true>(v, t_exact, bias, row, col0, pr.M, pr.N, sg, gst, p.g_scale, p.g_diag, acc_sp, acc_g, acc_gs);
+              loss_slab<true, false, true>(v, t_eff, bias, row, col0, pr.M, pr.N, sg, gst, p.g_scale, p.g_diag, acc_sp, acc_g, acc_gs);
           } else {
-            loss_slab<false, true, true>(v, t_exact, bias, row, col0, pr.M, pr.N, sg, gst, p.g_scale, p.g_diag, acc_sp, acc_g, acc_gs);
+            loss_slab<false, true, true>(v, t_eff, bias, row, col0, pr.M, pr.N, sg, gst, p.g_scale, p.g_diag, acc_sp, acc_g, acc_gs);
           }
         } else {
           out_slab(v, scale, row, col0, pr, fix);
@@ -735,7 +749,8 @@ siglip_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_consta
       // fixed-order reduction: lanes -> warp -> epilogue warps -> one slot per CTA (summed later in slot order)
       double d_sp = warp_sum(static_cast<double>(s_sp) - static_cast<double>(c_sp));
       double d_g = warp_sum(static_cast<double>(s_g) - static_cast<double>(c_g));
-      double d_gs = warp_sum(static_cast<double>(s_gs) - static_cast<double>(c_gs));
+      // sum g * acc -> sum g * <img, txt>
+      double d_gs = warp_sum(static_cast<double>(s_gs) - static_cast<double>(c_gs)) * static_cast<double>(s_scale);
       double* red = reinterpret_cast<double*>(smem_raw + (red_smem - smem_u32(smem_raw)));
       if (lane == 0) {
         red[warp * 3 + 0] = d_sp;
@@ -794,6 +809,10 @@ siglip_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_consta
       for (unsigned long long i = static_cast<unsigned long long>(blockIdx.x) * 64ull + (threadIdx.x - kAllocWarp * 32);
            i < n16; i += nthreads) {
         const uint4 v = src[i];
+        if (p.cvt_copy) {
+          dst[i] = v;
+          continue;
+        }
         const uint32_t w[4] = {v.x, v.y, v.z, v.w};
         uint32_t o[4];
 #pragma unroll
@@ -1062,6 +1081,18 @@ __device__ __forceinline__ void store8(void* base, size_t idx8, const float (&v)
   }
 }
 
+// fp16(v * scale), clamped to the fp16 range: the operand format of the fp32-input path
+__device__ __forceinline__ void store8_f16(void* base, size_t idx8, const float (&v)[8], float scale) {
+  uint32_t o[4];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const float lo = fminf(fmaxf(v[2 * q] * scale, -65504.f), 65504.f);
+    const float hi = fminf(fmaxf(v[2 * q + 1] * scale, -65504.f), 65504.f);
+    o[q] = pack_16x2<true>(lo, hi);
+  }
+  reinterpret_cast<uint4*>(base)[idx8] = make_uint4(o[0], o[1], o[2], o[3]);
+}
+
 __device__ __forceinline__ float warp_sum_f(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -1069,9 +1100,10 @@ __device__ __forceinline__ float warp_sum_f(float v) {
 }
 
 // xhat[r, :] = bf16(x[r, :] / max(||x[r, :]||, eps)),  inv_norm[r] = 1 / max(||x||, eps)      (F.normalize, eps 1e-12)
+// f16_scale > 0: xhat is written as fp16(xhat * f16_scale) instead of bf16 (fp32-input path)
 template <bool kInBf16>
 __global__ void normalize_fwd_kernel(const void* __restrict__ x, __nv_bfloat16* __restrict__ xhat,
-                                     float* __restrict__ inv_norm, int rows, int d8) {
+                                     float* __restrict__ inv_norm, int rows, int d8, float f16_scale) {
   const int warps_per_block = blockDim.x >> 5;
   const int lane = threadIdx.x & 31;
   for (int r = blockIdx.x * warps_per_block + (threadIdx.x >> 5); r < rows; r += gridDim.x * warps_per_block) {
@@ -1091,8 +1123,24 @@ __global__ void normalize_fwd_kernel(const void* __restrict__ x, __nv_bfloat16* 
       load8<kInBf16>(x, row8 + c, v);
 #pragma unroll
       for (int e = 0; e < 8; ++e) v[e] *= inv;
-      store8<true>(xhat, row8 + c, v);
+      if (f16_scale > 0.f)
+        store8_f16(xhat, row8 + c, v, f16_scale);
+      else
+        store8<true>(xhat, row8 + c, v);
     }
+  }
+}
+
+// dst = bf16(src) or fp16(src * f16_scale): the module's cast of fp32 embeddings to the operand format
+__global__ void convert_f32_kernel(const float* __restrict__ src, void* __restrict__ dst, size_t n8, float f16_scale) {
+  const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
+  for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n8; i += stride) {
+    float v[8];
+    load8<false>(src, i, v);
+    if (f16_scale > 0.f)
+      store8_f16(dst, i, v, f16_scale);
+    else
+      store8<true>(dst, i, v);
   }
 }
 
@@ -1288,12 +1336,17 @@ int launch_reduce_slots(void* out, int out_bf16, const float* const* slots_dev, 
 }
 
 int launch_normalize_fwd(const void* x, int in_bf16, __nv_bfloat16* xhat, float* inv_norm, int rows, int D,
-                         int num_sms, cudaStream_t stream) {
+                         float f16_scale, int num_sms, cudaStream_t stream) {
   const int grid = num_sms * 8, block = 256;
   if (in_bf16)
-    normalize_fwd_kernel<true><<<grid, block, 0, stream>>>(x, xhat, inv_norm, rows, D / 8);
+    normalize_fwd_kernel<true><<<grid, block, 0, stream>>>(x, xhat, inv_norm, rows, D / 8, f16_scale);
   else
-    normalize_fwd_kernel<false><<<grid, block, 0, stream>>>(x, xhat, inv_norm, rows, D / 8);
+    normalize_fwd_kernel<false><<<grid, block, 0, stream>>>(x, xhat, inv_norm, rows, D / 8, f16_scale);
+  return static_cast<int>(cudaGetLastError());
+}
+
+int launch_convert_f32(const float* src, void* dst, size_t n, float f16_scale, int num_sms, cudaStream_t stream) {
+  convert_f32_kernel<<<num_sms * 4, 256, 0, stream>>>(src, dst, n / 8, f16_scale);
   return static_cast<int>(cudaGetLastError());
 }
 

@@ -25,8 +25,10 @@ struct Problem {
   long long ldo;
   int out_bf16;
   const float* fix_vec;
-  const __nv_bfloat16* fix_mat;
+  const __nv_bfloat16* fix_mat;   // bf16 values, or (fix_f16) IEEE fp16 values scaled by 1 / fix_mat_scale
   long long ldx;
+  int fix_f16;
+  float fix_mat_scale;    // multiplies the decoded fix_mat value (1/16 for the fp16 x 16 embeddings; 0 = 1)
   const float* add_src;   // optional fp32 term (running dimg of the previous chunks)
   long long ld_add;
 };
@@ -37,6 +39,7 @@ struct KernelParams {
   // learnable scalars, device memory (reference: distributed_sigmoid_loss.py:11-12)
   const float* t_prime;
   const float* bias;
+  float s_scale;  // loss kernel: accumulator -> <img, txt> (2^-8 when both operands are fp16 x 16; 0 = 1)
   float inv_b;  // 1 / per-rank batch (reference divides by the LOCAL batch, distributed_sigmoid_loss.py:47)
   const float* grad_out;  // out kernel: optional device scalar multiplied into every gradient (autograd's grad_output)
   // epilogue of the "loss" kernel
@@ -64,6 +67,7 @@ struct KernelParams {
   uint4* cvt_dst[2];
   unsigned long long cvt_n16[2];
   float cvt_scale;
+  int cvt_copy;   // 1: the sources already are fp16 x cvt_scale (fp32-input path): plain copies
   // optional fp32 accumulate job of the same warps: acc_out = acc_in + acc_remote (acc_remote may be peer memory)
   const float4* acc_in;
   const float4* acc_remote;
@@ -105,7 +109,8 @@ int launch_reduce_slots(void* out, int out_bf16, const float* const* slots_dev, 
 
 // xhat = bf16(x / max(||x||, 1e-12)) row-wise, inv_norm[r] = 1 / max(||x_r||, 1e-12); x is fp32 or bf16 [rows, D]
 int launch_normalize_fwd(const void* x, int in_bf16, __nv_bfloat16* xhat, float* inv_norm, int rows, int D,
-                         int num_sms, cudaStream_t stream);
+                         float f16_scale, int num_sms, cudaStream_t stream);
+int launch_convert_f32(const float* src, void* dst, size_t n, float f16_scale, int num_sms, cudaStream_t stream);
 // dx = inv_norm * (dxhat - xhat <xhat, dxhat>), xhat recomputed in fp32 from x; dx has x's dtype
 int launch_normalize_bwd(const void* x, int in_bf16, const float* inv_norm, const void* dxhat, int grad_bf16, void* dx,
                          int rows, int D, int num_sms, cudaStream_t stream);

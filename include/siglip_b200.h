@@ -56,6 +56,11 @@ enum {
                                         all-reduce of the two parameters does, README.md:20,
                                         test_distributed_sigmoid_loss.py:79-83), exchanged through peer memory by a
                                         one-warp kernel; bit-identical on every rank. Collective: set on all ranks */
+  SIGLIP_OPT_INPUT_F16 = 13, /* 1: the img / txt buffers handed to siglip_forward / siglip_backward / siglip_fwd_bwd hold IEEE
+                                fp16 values 16*x (what siglip_convert_f32 and siglip_normalize_fwd then produce) instead of
+                                bf16: 11 significant bits for callers with fp32 embeddings (the reference's own test feeds fp32,
+                                test_distributed_sigmoid_loss.py:57-68; bf16 rounding of such inputs costs 1.7e-3 in the
+                                gradients, this format 2e-4). Same on all ranks. Default 0 */
   SIGLIP_OPT_BIDIR = 12, /* 1: visit the text chunks in the order r, r+1, r-1, r+2, r-2, ... (the order of the reference's
                             bidirectional exchange, rwightman_sigmoid_loss.py:75-107) instead of r, r+1, r+2, ...;
                             same pairs, same result up to fp32 summation order. Collective: set on all ranks */
@@ -110,12 +115,15 @@ int siglip_fwd_bwd(siglip_ctx* ctx, const void* img, const void* txt, const floa
 /*
  * L2 normalisation fused around the loss (the step the reference's callers run immediately before it:
  * F.normalize, test_distributed_sigmoid_loss.py:99-101, README.md:34). [B, D] rows, D % 8 == 0:
- *   fwd: xhat = bf16(x / max(||x||, 1e-12)) and inv_norm[r] = 1 / max(||x_r||, 1e-12); x is fp32 (in_bf16 = 0) or bf16
+ *   fwd: xhat = bf16(x / max(||x||, 1e-12)) (fp16(16 xhat) under SIGLIP_OPT_INPUT_F16) and inv_norm[r] = 1 / max(||x_r||, 1e-12); x is fp32 (in_bf16 = 0) or bf16
  *   bwd: dx = inv_norm * (dxhat - xhat <xhat, dxhat>) with xhat recomputed in fp32 from x; dxhat fp32 or bf16
  *        (grad_bf16), dx in x's dtype — autograd's backward of F.normalize composed with the loss gradients.
  */
 int siglip_normalize_fwd(siglip_ctx* ctx, const void* x, int in_bf16, void* xhat_bf16, float* inv_norm,
                          void* cuda_stream);
+/* [B, D] fp32 -> the 16-bit operand format the context currently expects (bf16, or fp16(16 x) under
+ * SIGLIP_OPT_INPUT_F16): the cast the module applies to fp32 embeddings (replaces `.to(bfloat16)`). */
+int siglip_convert_f32(siglip_ctx* ctx, const float* x_f32, void* out_16bit, void* cuda_stream);
 int siglip_normalize_bwd(siglip_ctx* ctx, const void* x, int in_bf16, const float* inv_norm, const void* dxhat,
                          int grad_bf16, void* dx, void* cuda_stream);
 

@@ -123,5 +123,5 @@ def torch_reference_fp32(img, txt_chunks, t_prime: float, bias: float, rank: int
         total = total + (-torch.nn.functional.logsigmoid(labels * logits)).sum()
     total = total / bsz
     total.backward()
-    return dict(loss=float(total), dimg=img32.grad, dtxt_chunks=[x.grad for x in chunks],
+    return dict(loss=float(total.detach()), dimg=img32.grad, dtxt_chunks=[x.grad for x in chunks],
                 dt_prime=float(tp.grad), dbias=float(bb.grad))

@@ -33,8 +33,13 @@ def pytest_collection_modifyitems(config, items):
             item.add_marker(skip)
 
 
-def golden_cases():
-    return sorted(f[:-4] for f in os.listdir(GOLDEN_DIR) if f.endswith(".npz"))
+def golden_cases(f32=False):
+    """Fixture names. f32=False: inputs are bf16-representable (what the bf16 path consumes exactly); f32=True: raw fp32
+    inputs as the reference's own test feeds them (the module's fp32-input path); f32="all": both."""
+    names = sorted(f[:-4] for f in os.listdir(GOLDEN_DIR) if f.endswith(".npz"))
+    if f32 == "all":
+        return names
+    return [n for n in names if ("_f32" in n) == bool(f32)]
 
 
 def load_golden(name):

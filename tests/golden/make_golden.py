@@ -38,10 +38,19 @@ CASES = [
     ("w5_b4_d32", 5, 4, 32, float(np.log(10)), -10.0),
     ("w2_b24_d40_warm", 2, 24, 40, float(np.log(25.0)), -4.5),  # logits near 0: exercises both sigmoid branches
     ("w1_b300_d136", 1, 300, 136, float(np.log(10)), -10.0),   # ragged vs the 128/256 tiles of the CUDA path
+    # raw fp32 inputs (NOT bf16-representable), the way the reference's own test feeds them
+    # (test_distributed_sigmoid_loss.py:57-68, 99-101): the fp32-input path of the CUDA module (fp16 x 16 operands)
+    ("w2_b32_d512_f32", 2, 32, 512, float(np.log(10)), -10.0),  # BASELINE.json configs[0], raw fp32
+    ("w1_b300_d136_f32", 1, 300, 136, float(np.log(10)), -10.0),
+    ("w3_b40_d64_f32_warm", 3, 40, 64, float(np.log(25.0)), -4.5),
 ]
 
 
-def global_inputs(world: int, b: int, d: int):
+def is_raw_f32(name: str) -> bool:
+    return "_f32" in name
+
+
+def global_inputs(world: int, b: int, d: int, raw_f32: bool = False):
     torch.manual_seed(42)
     img = torch.randn(world * b, d)
     torch.manual_seed(40)
@@ -49,10 +58,12 @@ def global_inputs(world: int, b: int, d: int):
     # L2-normalise (test_distributed_sigmoid_loss.py:99-101), then round to bf16-representable values and hand them to
     # the reference as fp32: "the reference in fp32 on the same bf16-rounded inputs" is the parity yardstick
     #  — the CUDA path consumes exactly these values as bf16.
+    if raw_f32:
+        return F.normalize(img), F.normalize(txt)
     return (F.normalize(img).to(torch.bfloat16).float(), F.normalize(txt).to(torch.bfloat16).float())
 
 
-def worker(rank: int, world: int, b: int, d: int, t_prime: float, bias: float, port: int, ret):
+def worker(rank: int, world: int, b: int, d: int, t_prime: float, bias: float, port: int, raw_f32: bool, ret):
     sys.path.insert(0, REF)
     from distributed_sigmoid_loss import DDPSigmoidLoss
     from rwightman_sigmoid_loss import SigLipLoss
@@ -61,7 +72,7 @@ def worker(rank: int, world: int, b: int, d: int, t_prime: float, bias: float, p
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     torch.set_num_threads(1)
-    img_all, txt_all = global_inputs(world, b, d)
+    img_all, txt_all = global_inputs(world, b, d, raw_f32)
     sl = slice(rank * b, (rank + 1) * b)
     out = {}
 
@@ -95,12 +106,16 @@ def worker(rank: int, world: int, b: int, d: int, t_prime: float, bias: float, p
 
 def main():
     port = 29610
+    only = set(sys.argv[1:])      # optional: names of the cases to (re)generate
     for (name, world, b, d, t_prime, bias) in CASES:
+        if only and name not in only:
+            continue
         mgr = mp.Manager()
         ret = mgr.dict()
-        mp.spawn(worker, args=(world, b, d, t_prime, bias, port, ret), nprocs=world, join=True)
+        raw = is_raw_f32(name)
+        mp.spawn(worker, args=(world, b, d, t_prime, bias, port, raw, ret), nprocs=world, join=True)
         port += 1
-        img_all, txt_all = global_inputs(world, b, d)
+        img_all, txt_all = global_inputs(world, b, d, raw)
         arrays = dict(img_all=img_all.numpy(), txt_all=txt_all.numpy(), world=np.int64(world), batch=np.int64(b),
                       dim=np.int64(d), t_prime=np.float64(t_prime), bias=np.float64(bias))
         for r in range(world):

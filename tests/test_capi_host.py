@@ -15,7 +15,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 def _header_symbols():
     text = open(os.path.join(ROOT, "include", "siglip_b200.h")).read()
-    return sorted(set(re.findall(r"\b(siglip_[a-z_]+)\s*\(", text)))
+    return sorted(set(re.findall(r"\b(siglip_[a-z_0-9]+)\s*\(", text)))
 
 
 def test_library_exports_every_declared_symbol():

@@ -17,7 +17,7 @@ def _close(a, b, rel=REL, abs_=ABS):
     return np.all(np.abs(a - b) <= abs_ + rel * np.abs(b))
 
 
-@pytest.mark.parametrize("name", golden_cases())
+@pytest.mark.parametrize("name", golden_cases("all"))
 @pytest.mark.parametrize("variant", ["ddp", "rw_bidir", "rw_uni"])
 def test_closed_form_matches_reference(name, variant):
     c = load_golden(name)
@@ -31,7 +31,7 @@ def test_closed_form_matches_reference(name, variant):
         assert abs(out[r]["dbias"] - float(ref["dbias"])) <= 2e-5 * abs(float(ref["dbias"])) + 1e-6
 
 
-@pytest.mark.parametrize("name", golden_cases())
+@pytest.mark.parametrize("name", golden_cases("all"))
 def test_port_step_matches_reference(name):
     """The op-for-op torch port (the timed CPU baseline) equals the reference module rank by rank. The text
     gradient of the port is per chunk; summing the chunk gradients over ranks reproduces all_gather's backward."""
@@ -74,7 +74,7 @@ def test_torch_reference_fp32_matches_reference(name):
 
 def test_variants_agree_with_each_other():
     """The reference's own invariant (test_sigmoid_loss_variants.py:112-113): all-gather variant == ring variant."""
-    for name in golden_cases():
+    for name in golden_cases("all"):
         c = load_golden(name)
         for r in range(c["world"]):
             a, b = c["variants"]["ddp"][r], c["variants"]["rw_bidir"][r]
