@@ -92,6 +92,28 @@ def main() -> int:
             dtxt=rel_f(b.grad.float().cpu(), torch.from_numpy(ref["dtxt"]))), tol=4e-3)
         eng.set_option(_capi.SIGLIP_OPT_OVERLAP_PULL, 1)
 
+    # ---- fp32 callers: raw fp32 inputs -> fp16(16 x) operands, text chunks exchanged in that format ---------------
+    if not args.skip_parity:
+        B, D, tp, bias = 160, 96, math.log(10.0), -10.0
+        g = torch.Generator().manual_seed(123)
+        img_all = torch.nn.functional.normalize(torch.randn(world * B, D, generator=g))
+        txt_all = torch.nn.functional.normalize(torch.randn(world * B, D, generator=g))
+        ref = closed_form(img_all.numpy(), txt_all.numpy(), tp, bias, world)[rank]
+        mod = DDPSigmoidLoss(B).to(dev)
+        a = img_all[rank * B:(rank + 1) * B].to(dev).requires_grad_(True)
+        b = txt_all[rank * B:(rank + 1) * B].to(dev).requires_grad_(True)
+        for rep in range(2):
+            a.grad = b.grad = mod.t_prime.grad = mod.bias.grad = None
+            lf = mod(a, b)
+            lf.backward()
+            torch.cuda.synchronize()
+            report(f"fp32 inputs (fp16x16 operands) B={B} D={D} rep{rep}", dict(
+                loss=abs(float(lf.detach()) - ref["loss"]) / abs(ref["loss"]),
+                dimg=rel_f(a.grad.cpu(), torch.from_numpy(ref["dimg"])),
+                dtxt=rel_f(b.grad.cpu(), torch.from_numpy(ref["dtxt"])),
+                dtp=abs(float(mod.t_prime.grad) - ref["dt_prime"]) / abs(ref["dt_prime"]),
+                db=abs(float(mod.bias.grad) - ref["dbias"]) / abs(ref["dbias"])))
+
     # ---- larger: fp32 autograd; dtxt reference summed over ranks ------------------------------------------
     B, D, tp, bias = 2048, 768, math.log(10.0), -10.0
     g = torch.Generator().manual_seed(1234 + rank)
