@@ -42,8 +42,9 @@ class ClockSampler:
     """SM clock / throttle reasons sampled DURING the timed region (B200_PROFILING.md) through NVML from a Python
     thread every ~5 ms (the C calls release the GIL); falls back to `nvidia-smi -lms` if pynvml is unavailable."""
 
-    def __init__(self, gpu_index: int):
+    def __init__(self, gpu_index: int, period_s: float = 0.005):
         self.gpu_index = gpu_index
+        self.period_s = period_s
         self.samples = []      # (sm_mhz, reasons_bitmask)
         self.max_mhz = None
         self._stop = threading.Event()
@@ -73,7 +74,7 @@ class ClockSampler:
                 self.samples.append((mhz, reasons))
             except Exception:
                 pass
-            time.sleep(0.005)
+            time.sleep(self.period_s)
 
     def mark(self):
         """Index of the next sample: call at the start of the timed region."""
@@ -303,7 +304,7 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    sampler = ClockSampler(local_rank)
+    sampler = ClockSampler(local_rank, args.clock_period_ms * 1e-3)
     if rank == 0:
         sampler.start()          # NVML thread, 5 ms period; samples from the timed region are reported
     # Warm-up: at least the requested steps AND >= 0.6 s of back-to-back steps, at every N. A B200 under tensor load
@@ -504,6 +505,7 @@ def main():
     ap.add_argument("--cta-group", type=int, default=int(os.environ.get("SIGLIP_CTA_GROUP", "2")))
     ap.add_argument("--cpu-sample-rows", type=int, default=2048)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--clock-period-ms", type=float, default=5.0, help="NVML clock / throttle-reason sampling period")
     ap.add_argument("--sustain-ms", type=float, default=600.0,
                     help="minimum GPU time of the warm-up (power-capped sustained clocks at every N); 0 = only --warmup")
     args = ap.parse_args()

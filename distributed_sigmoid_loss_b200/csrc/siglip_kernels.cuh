@@ -43,9 +43,9 @@ struct KernelParams {
   float inv_b;  // 1 / per-rank batch (reference divides by the LOCAL batch, distributed_sigmoid_loss.py:47)
   const float* grad_out;  // out kernel: optional device scalar multiplied into every gradient (autograd's grad_output)
   // epilogue of the "loss" kernel
-  __nv_bfloat16* G;  // [Bp, ldg] bf16 sigma terms, diagonal zeroed; may be null when store_g == 0
+  __nv_bfloat16* G;  // [Bp, ldg] 16-bit sigma terms (fp16 bits, x g_scale), diagonal zeroed; may be null when store_g == 0
   long long ldg;
-  float* g_diag;   // [B] fp32: -sigma(-z_ii), the positive-pair term kept out of the bf16 operand
+  float* g_diag;   // [B] fp32: -sigma(-z_ii), the positive-pair term kept out of the 16-bit operand
   int own_chunk;   // 1: this text chunk holds the positives of this rank's images
   int store_g;     // 0: forward only
   float g_scale;   // sigma is stored as fp16(sigma * g_scale): 2^14 keeps sigma in (3.7e-9, 1) inside fp16's normal range
@@ -85,7 +85,7 @@ int default_stages(int cta_group, int mode);
 int query_max_active_clusters(int cta_group);  // co-resident clusters of the out kernel (diagnostic)
 
 // Launch the warp-specialised persistent kernel. `stages` <= 0 selects the default pipeline depth.
-// tmG: store map of the sigma operand (loss mode; bf16 [B, B], box {32, 32}, 64B swizzle) — any valid map in out mode.
+// tmG: store map of the sigma operand (loss mode; 16-bit [B, B], box {32, 32}, 64B swizzle) — any valid map in out mode.
 // Returns cudaError_t as int.
 // mcast: 1 = every CTA (pair) loads its own operands; 2 = clusters of two CTAs (cta_group 1) or two MMA pairs
 // (cta_group 2: a 2x2 cluster) on vertically adjacent tiles share the B tile through TMA multicast; the K-major B map
