@@ -577,7 +577,7 @@ int backward_impl(siglip_ctx* c, const void* img, const void* txt, const float* 
 
 extern "C" {
 
-const char* siglip_version(void) { return "siglip_b200 0.2.0 sm_100a"; }
+const char* siglip_version(void) { return "siglip_b200 0.3.0 sm_100a"; }
 
 const char* siglip_last_error(void) { return g_last_error.c_str(); }
 
