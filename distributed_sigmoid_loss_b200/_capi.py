@@ -67,6 +67,7 @@ SIGLIP_OPT_EPI_SLEEP_LOSS_NS = 10
 SIGLIP_OPT_SYNC_SCALAR_GRADS = 11
 SIGLIP_OPT_BIDIR = 12
 SIGLIP_OPT_INPUT_F16 = 13
+SIGLIP_OPT_GRAD_TILE_N = 14
 
 _lib: Optional[ctypes.CDLL] = None
 

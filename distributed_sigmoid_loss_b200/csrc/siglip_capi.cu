@@ -142,6 +142,7 @@ struct siglip_ctx {
   int epi_sleep_loss_ns = 0;
   int sync_scalar_grads = 0;             // backward returns the mean over ranks of dt' / dbias
   int bidir = 0;                         // visiting order of the text chunks: r, r+1, r-1, r+2, r-2, ...
+  int grad_tile_n = 0;                   // column-tile width of the gradient kernel: 0 = choose, 128, 256
   int input_f16 = 0;                     // img / txt are fp16(x * kXScale) instead of bf16 (fp32-input path)
   int saved_f16 = 0;                     // format of the embeddings of the forward saved for backward
   // diagnostics, read from the environment once at context creation (see include/siglip_b200.h)
@@ -350,13 +351,31 @@ int run_grad_chunk(siglip_ctx* c, int k, const void* img, const __nv_bfloat16* t
   KernelParams p;
   memset(&p, 0, sizeof(p));
   p.nprob = 2;
+  // Column-tile width: 256, or 128 when that fills the waves of the persistent grid better (small B: B = 4096, D = 768
+  // is 96 tiles of 256 columns on 74 SM pairs = 2 waves for 1.3 waves of work, but 3 half-waves with 128 columns).
+  // A narrow tile streams the same sigma panel for half the flops and becomes L2->SM bound: it costs 0.66-0.70 of a
+  // full tile, measured (tools/tile_width_ab.py), so it pays only when the 256-wide grid leaves most of a wave empty.
+  int tile_n = c->grad_tile_n;
+  if (tile_n == 0) {
+    const long long units = c->num_sms / cg;
+    auto cost = [&](int tn) {   // waves x average tile cost (a 256-wide grid already runs a short last column as 128)
+      const long long cols = ceil_div(c->D, tn);
+      const int rem = c->D - static_cast<int>(cols - 1) * tn;
+      const double row_cost = (tn == 128) ? 0.70 * cols : (cols - 1) + (rem <= 128 ? 0.70 : 1.0);
+      const long long tiles = 2ll * ceil_div(c->B, tile_m) * cols;
+      return static_cast<double>((tiles + units - 1) / units) * row_cost / static_cast<double>(cols);
+    };
+    tile_n = (c->mcast == 1 && cost(128) < 0.97 * cost(256)) ? 128 : 256;
+  }
+  if (c->mcast != 1) tile_n = 256;
   for (int i = 0; i < 2; ++i) {
     Problem& pr = p.prob[i];
     pr.M = c->B;
     pr.N = c->D;
     pr.K = c->B;
+    pr.tile_n = tile_n;
     pr.tiles_m = ceil_div(c->B, tile_m);
-    pr.tiles_n = ceil_div(c->D, 256);
+    pr.tiles_n = ceil_div(c->D, tile_n);
     pr.b_mn = 1;
     pr.ab_f16 = 1;
     pr.acc_scale = 1.0f / (kGScale * kXScale);
@@ -689,6 +708,10 @@ int siglip_ctx_set_option(siglip_ctx* c, int option, int value) {
       return 0;
     case SIGLIP_OPT_EPI_SLEEP_LOSS_NS:
       c->epi_sleep_loss_ns = value < 0 ? 0 : value;
+      return 0;
+    case SIGLIP_OPT_GRAD_TILE_N:
+      if (value != 0 && value != 128 && value != 256) return fail(SIGLIP_ERR_INVALID, "grad_tile_n must be 0, 128 or 256");
+      c->grad_tile_n = value;
       return 0;
     case SIGLIP_OPT_INPUT_F16:
       c->input_f16 = value ? 1 : 0;

@@ -161,10 +161,22 @@ __device__ __forceinline__ int cluster_tiles(const Problem& pr) {
   return ((pr.tiles_m + kMC - 1) / kMC) * pr.tiles_n;
 }
 
-// Columns the MMA of column tile n_blk computes: 256, or 128 for a short last tile of the out kernel.
+// Column tiles of the out kernel (N-major B operand, no multicast) may be 128 wide instead of 256 (Problem::tile_n):
+// twice the tiles of half the work each, for shapes whose 256-wide tiles fill the last wave badly.
+template <int kMode, int kMC>
+__device__ __forceinline__ int tile_stride_n(const Problem& pr) {
+  if constexpr (kMode == kModeOut && kMC == 1) {
+    return (pr.tile_n == kTileN / 2 && pr.b_mn) ? kTileN / 2 : kTileN;
+  } else {
+    return kTileN;
+  }
+}
+
+// Columns the MMA of column tile n_blk computes: 256, or 128 for narrow tiles / a short last tile of the out kernel.
 template <int kMode, int kMC>
 __device__ __forceinline__ int tile_cols(const Problem& pr, int n_blk) {
   if constexpr (kMode == kModeOut && kMC == 1) {
+    if (tile_stride_n<kMode, kMC>(pr) == kTileN / 2) return kTileN / 2;
     return (pr.b_mn && pr.N - n_blk * kTileN <= kTileN / 2) ? kTileN / 2 : kTileN;
   } else {
     return kTileN;
@@ -473,7 +485,7 @@ siglip_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_consta
         // D = 1152 is 4.5 tiles of 256 — without this 10 % of the gradient MMA work would be padding
         const int n_cur = tile_cols<kMode, kMC>(pr, tc.n_blk);
         const int b_rows = n_cur / kCG;                               // B rows this CTA holds for the tile
-        const int n_idx = tc.n_blk * kTileN + static_cast<int>(cta_rank) * b_rows;
+        const int n_idx = tc.n_blk * tile_stride_n<kMode, kMC>(pr) + static_cast<int>(cta_rank) * b_rows;
         const uint32_t stage_tx = static_cast<uint32_t>(C::kABytes + b_rows * kBlockK * 2) * kCG;
         const int num_kb = (pr.K + kBlockK - 1) / kBlockK;
         const int a_mn = pr.a_mn, b_mn = pr.b_mn;
@@ -651,7 +663,7 @@ siglip_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_consta
       const TileCoord tc = decode_tile<kMC>(p, t, mc_rank);
       const Problem& pr = p.prob[tc.prob];
       const int row = tc.m_blk * C::kTileM + static_cast<int>(cta_rank) * kBlockM + row_in_cta;
-      const int col_base = tc.n_blk * kTileN + cgrp * kEpiCols;
+      const int col_base = tc.n_blk * tile_stride_n<kMode, kMC>(pr) + cgrp * kEpiCols;
       mbar_wait(tmem_full_bar(as), aphase, p.dbg, 4, t, as, p.epi_sleep_ns,
                 (p.wait_stats != nullptr && warp == 0) ? &w_epi : nullptr);
       tc_fence_after();

@@ -16,6 +16,7 @@ namespace siglip {
 struct Problem {
   int M, N, K;
   int tiles_m, tiles_n;
+  int tile_n;       // out kernel, N-major B: 128 = narrow column tiles (tiles_n = ceil(N / 128)); 0 / 256 = default
   int a_mn, b_mn;
   int ab_f16;       // both operands are IEEE fp16 (gradient contractions: scaled sigma operand x scaled embeddings)
   float acc_scale;  // multiplies the accumulator in the out epilogue (2^-k for a 2^k-scaled fp16 A operand)

@@ -61,6 +61,7 @@ enum {
                                 bf16: 11 significant bits for callers with fp32 embeddings (the reference's own test feeds fp32,
                                 test_distributed_sigmoid_loss.py:57-68; bf16 rounding of such inputs costs 1.7e-3 in the
                                 gradients, this format 2e-4). Same on all ranks. Default 0 */
+  SIGLIP_OPT_GRAD_TILE_N = 14, /* column-tile width of the gradient kernel: 0 (default) = choose by wave fill, 128, 256 */
   SIGLIP_OPT_BIDIR = 12, /* 1: visit the text chunks in the order r, r+1, r-1, r+2, r-2, ... (the order of the reference's
                             bidirectional exchange, rwightman_sigmoid_loss.py:75-107) instead of r, r+1, r+2, ...;
                             same pairs, same result up to fp32 summation order. Collective: set on all ranks */

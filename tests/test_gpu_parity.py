@@ -674,3 +674,24 @@ def test_fp32_inputs_multi_chunk_schedule_matches_raw_fp32_fixture(name):
         eng.close()
     for k in range(W):
         _check(f"dtxt owner {k}", dtxt_sum[k], c["variants"]["ddp"][k]["dtxt"])
+
+
+@pytest.mark.parametrize("shape", [(1000, 136), (1024, 384), (2048, 1152), (4096, 768)])
+@pytest.mark.parametrize("cg", [1, 2])
+def test_gradient_column_tile_width_does_not_change_the_result(shape, cg):
+    """SIGLIP_OPT_GRAD_TILE_N: 128-wide column tiles (chosen automatically when they fill the waves better, e.g.
+    B=4096 D=768) accumulate every output element over k in the same order as 256-wide ones: bitwise equal gradients."""
+    from distributed_sigmoid_loss_b200 import _capi
+    B, D = shape
+    img, txt = _synth(B, D, seed=11)
+    tp, b = _scal(math.log(10.0)), _scal(-10.0)
+    eng = _engine(B, D, cg)
+    out = {}
+    for tn in (256, 128, 0):
+        eng.set_option(_capi.SIGLIP_OPT_GRAD_TILE_N, tn)
+        _, dimg, dtxt, _, _ = eng.fwd_bwd(img, txt, tp, b)
+        torch.cuda.synchronize()
+        out[tn] = (dimg.clone(), dtxt.clone())
+    assert torch.equal(out[128][0], out[256][0]) and torch.equal(out[128][1], out[256][1])
+    assert torch.equal(out[0][0], out[256][0]) and torch.equal(out[0][1], out[256][1])
+    eng.close()
