@@ -157,6 +157,7 @@ struct siglip_ctx {
   float* dimg_acc = nullptr;             // [B, D] fp32 running dimg over the chunks (world > 1)
   float* dtxt_acc = nullptr;             // [B, D] fp32 running sum of the peers' contributions (world > 1)
   double* partials = nullptr;            // [num_sms][4]
+  unsigned int* fin_counter = nullptr;   // ticket counter of the loss kernel's last-CTA finalisation
   unsigned int* flags = nullptr;         // [kFlagKinds][kMaxWorld]
   float* scalars = nullptr;              // [16] device scalars: host API staging, saved dt'/dbias of the last forward
   // peers (index = rank); own entries point at local memory
@@ -233,8 +234,14 @@ struct PullJob {
 
 // The loss kernel over the text chunk of step k: S = img @ txt_c^T on tcgen05, fused scale/bias/log-sigmoid/reduce.
 // save: also write the sigma operand G[k] (+ g_diag on the own chunk) and the fp16 copies the gradient kernel needs.
+struct FinJob {   // last chunk of a forward: the loss kernel's last CTA writes the results
+  float* loss = nullptr;
+  float* dt_prime = nullptr;
+  float* dbias = nullptr;
+};
+
 int run_loss_chunk(siglip_ctx* c, int k, const void* img, const __nv_bfloat16* txt_c, const float* t_prime,
-                   const float* bias, bool save, const PullJob& pull, cudaStream_t st) {
+                   const float* bias, bool save, const PullJob& pull, const FinJob* fin, cudaStream_t st) {
   const int cg = c->cta_group;
   const int tile_m = 128 * cg;
   const bool own = (k == 0);
@@ -271,7 +278,13 @@ int run_loss_chunk(siglip_ctx* c, int k, const void* img, const __nv_bfloat16* t
   p.store_g = save ? 1 : 0;
   p.g_scale = kGScale;
   p.partials = c->partials;
-  p.accumulate_partials = 1;  // the partials are zeroed at the start of every forward
+  p.accumulate_partials = (k > 0) ? 1 : 0;  // the first chunk of a forward overwrites every slot of the grid
+  if (fin != nullptr) {
+    p.fin_counter = c->fin_counter;
+    p.fin_loss = fin->loss;
+    p.fin_dt_prime = fin->dt_prime;
+    p.fin_dbias = fin->dbias;
+  }
   p.dbg = c->dbg_dev;
   p.pull_src = reinterpret_cast<const uint4*>(pull.src);
   p.pull_dst = reinterpret_cast<uint4*>(pull.dst);
@@ -337,7 +350,7 @@ struct FoldJob {   // dtxt_acc = (in ? in : 0) + remote   by the idle warps of a
 //   prob 1: dtxt_c  = g (t/B) (G^T @ img  [+ g_diag * img])          A = G M-major,  B = img16 N-major
 int run_grad_chunk(siglip_ctx* c, int k, const void* img, const __nv_bfloat16* txt_c, const float* t_prime,
                    const float* grad_out, const float* dimg_add, void* dimg_out, bool dimg_bf16, void* dtxt_out,
-                   bool dtxt_bf16, const FoldJob& fold, cudaStream_t st) {
+                   bool dtxt_bf16, const FoldJob& fold, float* sc_dt_prime, float* sc_dbias, cudaStream_t st) {
   const int cg = c->cta_group;
   const int tile_m = 128 * cg;
   const bool own = (k == 0);
@@ -404,6 +417,11 @@ int run_grad_chunk(siglip_ctx* c, int k, const void* img, const __nv_bfloat16* t
     p.acc_wait_value = fold.value;
   }
   p.epi_sleep_ns = static_cast<unsigned int>(c->epi_sleep_grad_ns);
+  if (sc_dt_prime != nullptr || sc_dbias != nullptr) {   // backward of the two scalars rides on this launch
+    p.sc_saved = c->scalars + kSavedScalars;
+    p.sc_dt_prime = sc_dt_prime;
+    p.sc_dbias = sc_dbias;
+  }
   p.t_prime = t_prime;
   p.grad_out = grad_out;
   p.inv_b = 1.0f / static_cast<float>(c->B);
@@ -475,8 +493,12 @@ int forward_impl(siglip_ctx* c, const void* img, const void* txt, const float* t
     if ((rc = signal_peers(c, 0, s, st))) return rc;
     own_txt = c->txt_all + r * chunk_elems;
   }
-  CKI(siglip::launch_zero_partials(c->partials, c->num_sms, st));
-  c->launches++;
+  // (every launch of one forward has the same grid: chunk 0 overwrites its slots, the last CTA sums exactly those)
+  // loss, and (for backward) dt' / dbias for an upstream gradient of 1: written by the last CTA of the last chunk
+  FinJob fin;
+  fin.loss = loss;
+  fin.dt_prime = save ? c->scalars + kSavedScalars : nullptr;
+  fin.dbias = save ? c->scalars + kSavedScalars + 1 : nullptr;
   for (int k = 0; k < W; ++k) {
     const int cidx = step_owner(c, r, k);
     const __nv_bfloat16* txt_c = (k == 0) ? own_txt : c->txt_all + cidx * chunk_elems;
@@ -495,13 +517,9 @@ int forward_impl(siglip_ctx* c, const void* img, const void* txt, const float* t
         pull = PullJob();
       }
     }
-    if ((rc = run_loss_chunk(c, k, img, txt_c, t_prime, bias, save, pull, st))) return rc;
+    if ((rc = run_loss_chunk(c, k, img, txt_c, t_prime, bias, save, pull, (k == W - 1) ? &fin : nullptr, st)))
+      return rc;
   }
-  // loss, and (for backward) dt' / dbias for an upstream gradient of 1
-  CKI(siglip::launch_finalize(c->partials, c->num_sms, t_prime, 1.0f / static_cast<float>(c->B), loss,
-                              save ? c->scalars + kSavedScalars : nullptr,
-                              save ? c->scalars + kSavedScalars + 1 : nullptr, st));
-  c->launches++;
   if (W > 1) {
     if ((rc = signal_peers(c, 2, s, st))) return rc;
   }
@@ -558,8 +576,12 @@ int backward_impl(siglip_ctx* c, const void* img, const void* txt, const float* 
       fold.flag = c->flags + 1 * kMaxWorld + pr;
       fold.value = base + static_cast<unsigned int>(j - 1);
     }
+    // dt' / dbias = saved * grad_out is written by the last gradient launch (the in-kernel mean over ranks, when
+    // enabled, is a separate one-warp kernel below)
+    const bool scalars_here = last && !(W > 1 && c->sync_scalar_grads);
     if ((rc = run_grad_chunk(c, k, img, txt_c, t_prime, grad_out, dimg_add, dimg_out, last && c->grad_bf16, dtxt_out,
-                             W == 1 && c->grad_bf16, fold, st)))
+                             W == 1 && c->grad_bf16, fold, scalars_here ? dt_prime : nullptr,
+                             scalars_here ? dbias : nullptr, st)))
       return rc;
     if (W > 1 && (!last || !c->overlap_reduce)) {
       if ((rc = signal_peers(c, 1, base + static_cast<unsigned int>(j), st))) return rc;
@@ -583,9 +605,6 @@ int backward_impl(siglip_ctx* c, const void* img, const void* txt, const float* 
                                          reinterpret_cast<float*>(c->flags + kMailboxOffset), c->mailbox_ptrs_dev,
                                          c->signal_ptrs_dev + 4 * W, c->flags + 4 * kMaxWorld, W, n, dt_prime, dbias,
                                          c->dbg_dev, st));
-    c->launches++;
-  } else if (dt_prime != nullptr || dbias != nullptr) {
-    CKI(siglip::launch_scale_scalars(c->scalars + kSavedScalars, grad_out, dt_prime, dbias, st));
     c->launches++;
   }
   CK(cudaGetLastError());
@@ -651,6 +670,8 @@ int siglip_ctx_create(siglip_ctx** out, int device, int rank, int world, int B, 
   CK(alloc(reinterpret_cast<void**>(&c->img16), chunk_elems * sizeof(__nv_bfloat16)));
   CK(alloc(reinterpret_cast<void**>(&c->txt16), chunk_elems * world * sizeof(__nv_bfloat16)));
   CK(alloc(reinterpret_cast<void**>(&c->partials), static_cast<size_t>(c->num_sms) * 4 * sizeof(double)));
+  CK(alloc(reinterpret_cast<void**>(&c->fin_counter), sizeof(unsigned int)));
+  CK(cudaMemset(c->fin_counter, 0, sizeof(unsigned int)));
   CK(alloc(reinterpret_cast<void**>(&c->flags), kFlagBytes));
   CK(alloc(reinterpret_cast<void**>(&c->scalars), 16 * sizeof(float)));
   CK(cudaMemset(c->flags, 0, kFlagBytes));
@@ -1188,6 +1209,7 @@ void siglip_ctx_destroy(siglip_ctx* c) {
   cudaFree(c->dtxt_acc);
   cudaFree(c->final_ptrs_dev);
   cudaFree(c->partials);
+  cudaFree(c->fin_counter);
   cudaFree(c->flags);
   cudaFree(c->scalars);
   cudaFree(c->reduce_ptrs_dev);

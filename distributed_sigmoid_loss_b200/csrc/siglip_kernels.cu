@@ -650,6 +650,14 @@ siglip_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_consta
     // was 11 % of the loss kernel's stall samples (the fp64 pipe of this part is narrow); fp64 only at the very end
     float s_sp = 0.f, s_g = 0.f, s_gs = 0.f, c_sp = 0.f, c_g = 0.f, c_gs = 0.f;
     long long w_epi = 0;
+    if constexpr (kMode == kModeOut) {
+      // backward of the two scalars: saved (upstream gradient 1) * grad_out, by one thread of the launch
+      if (blockIdx.x == 0 && threadIdx.x == 0 && p.sc_saved != nullptr) {
+        const float g = (p.grad_out != nullptr) ? *p.grad_out : 1.0f;
+        if (p.sc_dt_prime) *p.sc_dt_prime = p.sc_saved[0] * g;
+        if (p.sc_dbias) *p.sc_dbias = p.sc_saved[1] * g;
+      }
+    }
     const uint64_t g_store_policy = l2_policy_evict_first();
     const long long epi_start = clock_cycles();
     int as = 0;
@@ -770,22 +778,54 @@ siglip_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_consta
         red[warp * 3 + 2] = d_gs;
       }
       named_barrier_sync(1, kNumEpiWarps * 32);
-      if (threadIdx.x == 0) {
-        double s0 = 0.0, s1 = 0.0, s2 = 0.0;
-        for (int w = 0; w < kNumEpiWarps; ++w) {
-          s0 += red[w * 3 + 0];
-          s1 += red[w * 3 + 1];
-          s2 += red[w * 3 + 2];
+      if (warp == 0) {
+        unsigned int ticket = 0;
+        if (lane == 0) {
+          double s0 = 0.0, s1 = 0.0, s2 = 0.0;
+          for (int w = 0; w < kNumEpiWarps; ++w) {
+            s0 += red[w * 3 + 0];
+            s1 += red[w * 3 + 1];
+            s2 += red[w * 3 + 2];
+          }
+          double* slot = p.partials + 4ll * blockIdx.x;
+          if (p.accumulate_partials) {
+            s0 += slot[0];
+            s1 += slot[1];
+            s2 += slot[2];
+          }
+          slot[0] = s0;
+          slot[1] = s1;
+          slot[2] = s2;
+          if (p.fin_counter != nullptr) {
+            __threadfence();                              // the slot before the ticket
+            ticket = atomicAdd(p.fin_counter, 1u);
+          }
         }
-        double* slot = p.partials + 4ll * blockIdx.x;
-        if (p.accumulate_partials) {
-          s0 += slot[0];
-          s1 += slot[1];
-          s2 += slot[2];
+        if (p.fin_counter != nullptr) {
+          ticket = __shfl_sync(0xffffffffu, ticket, 0);
+          if (ticket == gridDim.x - 1) {
+            // last CTA of the forward's last loss kernel: every slot is final. One warp, slot order and a fixed
+            // shuffle tree => bitwise reproducible for a fixed grid (the former finalize kernel, without its launch)
+            __threadfence();
+            double f0 = 0.0, f1 = 0.0, f2 = 0.0;
+            for (unsigned int i = lane; i < gridDim.x; i += 32) {
+              f0 += __ldcg(p.partials + 4ll * i + 0);
+              f1 += __ldcg(p.partials + 4ll * i + 1);
+              f2 += __ldcg(p.partials + 4ll * i + 2);
+            }
+            f0 = warp_sum(f0);
+            f1 = warp_sum(f1);
+            f2 = warp_sum(f2);
+            if (lane == 0) {
+              const double inv_b = static_cast<double>(p.inv_b);
+              if (p.fin_loss) *p.fin_loss = static_cast<float>(f0 * inv_b);
+              if (p.fin_dbias) *p.fin_dbias = static_cast<float>(f1 * inv_b);
+              if (p.fin_dt_prime)
+                *p.fin_dt_prime = static_cast<float>(exp(static_cast<double>(*p.t_prime)) * f2 * inv_b);
+              *p.fin_counter = 0u;                        // ready for the next forward
+            }
+          }
         }
-        slot[0] = s0;
-        slot[1] = s1;
-        slot[2] = s2;
       }
     }
   } else {
@@ -886,41 +926,6 @@ siglip_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_consta
 // -------------------------------------------------------------------------------------------------
 // small helper kernels
 // -------------------------------------------------------------------------------------------------
-__global__ void finalize_kernel(const double* __restrict__ partials, int nparts, const float* __restrict__ t_prime,
-                                float inv_b, float* loss, float* dt_prime, float* dbias) {
-  // one warp; fixed summation order => bitwise reproducible for a fixed grid
-  double s0 = 0.0, s1 = 0.0, s2 = 0.0;
-  for (int i = threadIdx.x; i < nparts; i += 32) {
-    s0 += partials[4ll * i + 0];
-    s1 += partials[4ll * i + 1];
-    s2 += partials[4ll * i + 2];
-  }
-  s0 = warp_sum(s0);
-  s1 = warp_sum(s1);
-  s2 = warp_sum(s2);
-  if (threadIdx.x == 0) {
-    const double t = exp(static_cast<double>(*t_prime));
-    if (loss) *loss = static_cast<float>(s0 * inv_b);
-    if (dbias) *dbias = static_cast<float>(s1 * inv_b);
-    if (dt_prime) *dt_prime = static_cast<float>(t * s2 * inv_b);
-  }
-}
-
-// backward of the two scalars: out = saved * grad_out
-__global__ void scale_scalars_kernel(const float* __restrict__ saved, const float* __restrict__ g, float* dt_prime,
-                                     float* dbias) {
-  const float s = (g != nullptr) ? *g : 1.0f;
-  if (threadIdx.x == 0) {
-    if (dt_prime) *dt_prime = saved[0] * s;
-    if (dbias) *dbias = saved[1] * s;
-  }
-}
-
-__global__ void zero_partials_kernel(double* partials, int n) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) partials[i] = 0.0;
-}
-
 __global__ void reduce_slots_kernel(void* __restrict__ out, int out_bf16, const float* const* __restrict__ slots,
                                     int nslots, size_t n4) {
   const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
@@ -1323,23 +1328,6 @@ int launch_gemm(int cta_group, int mode, int stages, int mcast, const CUtensorMa
   }
 }
 #undef SIGLIP_LAUNCH
-
-int launch_finalize(const double* partials, int nparts, const float* t_prime, float inv_b, float* loss,
-                    float* dt_prime, float* dbias, cudaStream_t stream) {
-  finalize_kernel<<<1, 32, 0, stream>>>(partials, nparts, t_prime, inv_b, loss, dt_prime, dbias);
-  return static_cast<int>(cudaGetLastError());
-}
-
-int launch_scale_scalars(const float* saved, const float* g, float* dt_prime, float* dbias, cudaStream_t stream) {
-  scale_scalars_kernel<<<1, 32, 0, stream>>>(saved, g, dt_prime, dbias);
-  return static_cast<int>(cudaGetLastError());
-}
-
-int launch_zero_partials(double* partials, int nparts, cudaStream_t stream) {
-  const int n = nparts * 4;
-  zero_partials_kernel<<<(n + 255) / 256, 256, 0, stream>>>(partials, n);
-  return static_cast<int>(cudaGetLastError());
-}
 
 int launch_reduce_slots(void* out, int out_bf16, const float* const* slots_dev, int nslots, size_t n, int num_sms,
                         cudaStream_t stream) {

@@ -52,6 +52,16 @@ struct KernelParams {
   float g_scale;   // sigma is stored as fp16(sigma * g_scale): 2^14 keeps sigma in (3.7e-9, 1) inside fp16's normal range
   double* partials;  // [gridDim.x][4] : sum softplus, sum g, sum g*s, (unused)
   int accumulate_partials;
+  // loss kernel of the LAST chunk of a forward: the CTA that finishes last (ticket counter) adds the per-CTA slots in
+  // slot order and writes loss (and, when saving for backward, dt' / dbias for an upstream gradient of 1)
+  unsigned int* fin_counter;   // null = no finalisation in this launch
+  float* fin_loss;
+  float* fin_dt_prime;         // may be null
+  float* fin_dbias;            // may be null
+  // gradient kernel: dt' / dbias of the backward = saved value * grad_out, written by one thread (null = skip)
+  const float* sc_saved;       // [2]
+  float* sc_dt_prime;
+  float* sc_dbias;
   DebugRecord* dbg;
   unsigned long long* wait_stats;  // optional [gridDim.x][4]: producer empty-wait, MMA full-wait, MMA tmem-wait, MMA loop cycles
   unsigned int epi_sleep_ns;  // back-off of the epilogue warps while they wait for an accumulator (0 = spin)
@@ -96,14 +106,6 @@ int launch_gemm(int cta_group, int mode, int stages, int mcast, const CUtensorMa
                 int num_sms, cudaStream_t stream);
 
 // loss = inv_b * S0 ; dbias = inv_b * S1 ; dt_prime = exp(t') * inv_b * S2  (S* = fixed-order sums of partials)
-int launch_finalize(const double* partials, int nparts, const float* t_prime, float inv_b, float* loss,
-                    float* dt_prime, float* dbias, cudaStream_t stream);
-
-int launch_zero_partials(double* partials, int nparts, cudaStream_t stream);
-
-// dt_prime = saved[0] * (*g), dbias = saved[1] * (*g)   (g == nullptr: 1)
-int launch_scale_scalars(const float* saved, const float* g, float* dt_prime, float* dbias, cudaStream_t stream);
-
 // dtxt[j, d] = sum_r slots[r][j, d]   (slots may be peer-mapped pointers; fp32; n = elements)
 int launch_reduce_slots(void* out, int out_bf16, const float* const* slots_dev, int nslots, size_t n, int num_sms,
                         cudaStream_t stream);
