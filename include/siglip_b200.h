@@ -49,6 +49,7 @@ enum {
   SIGLIP_OPT_STAGES_LOSS = 4,  /* TMA->MMA pipeline depth of the loss kernel (0 = default) */
   SIGLIP_OPT_STAGES_GRAD = 5,  /* ... of the gradient kernel */
   SIGLIP_OPT_MCAST = 6,        /* 2: vertically adjacent tiles share the B tile by TMA multicast (cta_group 2: 2x2 clusters); default 1 */
+  SIGLIP_OPT_GRAD_BF16 = 7,     /* 1: siglip_fwd_bwd writes dimg / dtxt as bf16 [B, D] (the dtype autograd returns for bf16 inputs); default 0 = fp32 */
   SIGLIP_OPT_OVERLAP_REDUCE = 8, /* 1 (default): fold the peers' dtxt contributions in step by step inside the gradient kernels; 0: one reduction at the end */
   SIGLIP_OPT_EPI_SLEEP_GRAD_NS = 9, /* nanosleep back-off of the epilogue warps while they wait for an accumulator (gradient kernel) */
   SIGLIP_OPT_EPI_SLEEP_LOSS_NS = 10, /* ... (loss kernel) */
@@ -56,16 +57,15 @@ enum {
                                         all-reduce of the two parameters does, README.md:20,
                                         test_distributed_sigmoid_loss.py:79-83), exchanged through peer memory by a
                                         one-warp kernel; bit-identical on every rank. Collective: set on all ranks */
+  SIGLIP_OPT_BIDIR = 12, /* 1: visit the text chunks in the order r, r+1, r-1, r+2, r-2, ... (the order of the reference's
+                            bidirectional exchange, rwightman_sigmoid_loss.py:75-107) instead of r, r+1, r+2, ...;
+                            same pairs, same result up to fp32 summation order. Collective: set on all ranks */
   SIGLIP_OPT_INPUT_F16 = 13, /* 1: the img / txt buffers handed to siglip_forward / siglip_backward / siglip_fwd_bwd hold IEEE
                                 fp16 values 16*x (what siglip_convert_f32 and siglip_normalize_fwd then produce) instead of
                                 bf16: 11 significant bits for callers with fp32 embeddings (the reference's own test feeds fp32,
                                 test_distributed_sigmoid_loss.py:57-68; bf16 rounding of such inputs costs 1.7e-3 in the
                                 gradients, this format 2e-4). Same on all ranks. Default 0 */
-  SIGLIP_OPT_GRAD_TILE_N = 14, /* column-tile width of the gradient kernel: 0 (default) = choose by wave fill, 128, 256 */
-  SIGLIP_OPT_BIDIR = 12, /* 1: visit the text chunks in the order r, r+1, r-1, r+2, r-2, ... (the order of the reference's
-                            bidirectional exchange, rwightman_sigmoid_loss.py:75-107) instead of r, r+1, r+2, ...;
-                            same pairs, same result up to fp32 summation order. Collective: set on all ranks */
-  SIGLIP_OPT_GRAD_BF16 = 7     /* 1: siglip_fwd_bwd writes dimg / dtxt as bf16 [B, D] (the dtype autograd returns for bf16 inputs); default 0 = fp32 */
+  SIGLIP_OPT_GRAD_TILE_N = 14 /* column-tile width of the gradient kernel: 0 (default) = choose by wave fill, 128, 256 */
 };
 
 /* Library / build identification: "siglip_b200 <version> sm_100a". */
