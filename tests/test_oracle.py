@@ -94,3 +94,36 @@ def test_world_invariance():
     dtxt = np.concatenate([m["dtxt"] for m in multi]) / W
     assert np.allclose(dimg, single["dimg"], rtol=1e-9, atol=1e-12)
     assert np.allclose(dtxt, single["dtxt"], rtol=1e-9, atol=1e-12)
+
+
+def test_closed_form_equals_port_on_random_problems():
+    """Property check beyond the fixtures: for random (W, B, D, t', bias) — cold, warm and saturated logits — the fp64
+    closed form and the reference's op sequence (fp64 inputs through torch autograd) agree to 1e-9."""
+    hyp = pytest.importorskip("hypothesis")
+    from hypothesis import given, settings, strategies as st
+
+    @settings(max_examples=25, deadline=None, derandomize=True)
+    @given(W=st.integers(1, 4), B=st.integers(1, 9), D=st.integers(1, 12), tp=st.floats(-1.0, 4.5),
+           bias=st.floats(-15.0, 3.0), seed=st.integers(0, 10_000))
+    def check(W, B, D, tp, bias, seed):
+        g = torch.Generator().manual_seed(seed)
+        img_all = torch.nn.functional.normalize(torch.randn(W * B, D, generator=g, dtype=torch.float64), dim=-1)
+        txt_all = torch.nn.functional.normalize(torch.randn(W * B, D, generator=g, dtype=torch.float64), dim=-1)
+        out = closed_form(img_all.numpy(), txt_all.numpy(), tp, bias, W)
+        dtxt_sum = torch.zeros_like(txt_all)
+        for r in range(W):
+            img = img_all[r * B:(r + 1) * B].clone().requires_grad_(True)
+            chunks = [txt_all[k * B:(k + 1) * B].clone().requires_grad_(True) for k in range(W)]
+            t = torch.tensor(tp, dtype=torch.float64, requires_grad=True)
+            b = torch.tensor(bias, dtype=torch.float64, requires_grad=True)
+            loss = port_step(img, chunks, t, b, r)
+            assert abs(float(loss) - out[r]["loss"]) <= 1e-9 * max(1.0, abs(out[r]["loss"]))
+            assert _close(img.grad.numpy(), out[r]["dimg"], rel=1e-9, abs_=1e-12)
+            assert abs(float(t.grad) - out[r]["dt_prime"]) <= 1e-9 * max(1.0, abs(out[r]["dt_prime"]))
+            assert abs(float(b.grad) - out[r]["dbias"]) <= 1e-9 * max(1.0, abs(out[r]["dbias"]))
+            for k in range(W):
+                dtxt_sum[k * B:(k + 1) * B] += chunks[k].grad
+        for r in range(W):
+            assert _close(dtxt_sum[r * B:(r + 1) * B].numpy(), out[r]["dtxt"], rel=1e-9, abs_=1e-12)
+
+    check()
