@@ -5,4 +5,4 @@ from . import _capi
 from .loss import DDPSigmoidLoss, SigLipLoss, SigmoidLoss, SigmoidLossEngine, chunk_schedule
 
 __all__ = ["DDPSigmoidLoss", "SigmoidLoss", "SigLipLoss", "SigmoidLossEngine", "chunk_schedule", "_capi"]
-__version__ = "0.1.0"
+__version__ = "0.4.0"

@@ -21,6 +21,7 @@ EXPORTED_SYMBOLS = (
     "siglip_last_error",
     "siglip_device_count",
     "siglip_ctx_create",
+    "siglip_ctx_create_uneven",
     "siglip_ctx_set_option",
     "siglip_ctx_workspace_bytes",
     "siglip_ctx_handle_bytes",
@@ -30,10 +31,12 @@ EXPORTED_SYMBOLS = (
     "siglip_backward",
     "siglip_ctx_saved_generation",
     "siglip_fwd_bwd",
+    "siglip_fwd_bwd_scaled",
     "siglip_fwd",
     "siglip_fwd_bwd_host",
     "siglip_convert_f32",
     "siglip_host_submit",
+    "siglip_host_submit_grads",
     "siglip_host_wait",
     "siglip_scale",
     "siglip_normalize_fwd",
@@ -45,6 +48,8 @@ EXPORTED_SYMBOLS = (
     "siglip_debug_loopback",
     "siglip_debug_set_text_chunk",
     "siglip_debug_get_slot",
+    "siglip_debug_set_mailbox",
+    "siglip_ctx_aux_trace",
     "siglip_ctx_destroy",
 )
 
@@ -68,6 +73,10 @@ SIGLIP_OPT_SYNC_SCALAR_GRADS = 11
 SIGLIP_OPT_BIDIR = 12
 SIGLIP_OPT_INPUT_F16 = 13
 SIGLIP_OPT_GRAD_TILE_N = 14
+SIGLIP_OPT_PEER_TIMEOUT_MS = 15
+SIGLIP_OPT_INKERNEL_SYNC = 16
+SIGLIP_OPT_SPLIT_K = 17
+SIGLIP_OPT_AUX_TRACE = 18
 
 _lib: Optional[ctypes.CDLL] = None
 
@@ -124,6 +133,17 @@ def lib() -> ctypes.CDLL:
     L.siglip_ctx_saved_generation.restype = ctypes.c_ulonglong
     L.siglip_fwd_bwd.argtypes = [vp] * 11
     L.siglip_fwd_bwd.restype = ci
+    L.siglip_fwd_bwd_scaled.argtypes = [vp] * 12
+    L.siglip_fwd_bwd_scaled.restype = ci
+    L.siglip_ctx_create_uneven.argtypes = [ctypes.POINTER(vp), ci, ci, ci, ctypes.POINTER(ci), ci]
+    L.siglip_ctx_create_uneven.restype = ci
+    L.siglip_host_submit_grads.argtypes = [vp, vp, vp, ctypes.c_float, ctypes.c_float, vp, vp,
+                                           ctypes.POINTER(ctypes.c_ulonglong), vp]
+    L.siglip_host_submit_grads.restype = ci
+    L.siglip_debug_set_mailbox.argtypes = [vp, ci, ctypes.c_float, ctypes.c_float]
+    L.siglip_debug_set_mailbox.restype = ci
+    L.siglip_ctx_aux_trace.argtypes = [vp, vp, ci, ctypes.POINTER(ci)]
+    L.siglip_ctx_aux_trace.restype = ci
     L.siglip_fwd.argtypes = [vp] * 7
     L.siglip_fwd.restype = ci
     L.siglip_fwd_bwd_host.argtypes = [vp, vp, vp, ctypes.c_float, ctypes.c_float, vp, vp, vp, vp, vp, vp]

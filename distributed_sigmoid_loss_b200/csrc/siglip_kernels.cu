@@ -104,38 +104,57 @@ __device__ __forceinline__ double warp_sum(double v) {
   return v;
 }
 
-// Bounded wait of the two auxiliary warps (64 threads) of a CTA on a flag written by a peer GPU (st.release.sys):
-// ONE thread per CTA polls (acquire, system scope) with a back-off — thousands of threads hammering one L2 line slowed
-// the MMA operand traffic of the whole kernel — then the 64 threads meet on a named barrier. Traps after 20 s.
-__device__ __forceinline__ void wait_peer_flag(const volatile unsigned int* flag, unsigned int value, DebugRecord* dbg,
-                                               unsigned int site) {
+// Bounded wait of the two auxiliary warps (64 threads) of a CTA on `n` consecutive flags written by peer GPUs
+// (st.release.sys): ONE thread per CTA polls (acquire, system scope) with a back-off — thousands of threads hammering
+// one L2 line slowed the MMA operand traffic of the whole kernel — then the 64 threads meet on a named barrier.
+// Traps after timeout_ns (SIGLIP_OPT_PEER_TIMEOUT_MS: minutes by default, like a process-group timeout — a peer may
+// legitimately be late by a checkpoint save or an evaluation pass).
+__device__ __forceinline__ void wait_peer_flags(const volatile unsigned int* flags, int n, unsigned int value,
+                                                unsigned long long timeout_ns, DebugRecord* dbg, unsigned int site) {
   if (threadIdx.x == kAllocWarp * 32) {
     uint64_t t0 = 0;
     uint32_t spins = 0;
-    while (true) {
-      unsigned int v;
-      asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
-      if (v >= value) break;
-      __nanosleep(200);
-      if ((++spins & 0xffu) == 0) {
-        const uint64_t now = globaltimer_ns();
-        if (t0 == 0) t0 = now;
-        if (now - t0 > 20000000000ull) {
-          if (dbg != nullptr) {
-            dbg->block = blockIdx.x;
-            dbg->thread = threadIdx.x;
-            dbg->aux0 = v;
-            dbg->aux1 = value;
-            dbg->code = site;
-            __threadfence_system();
+    for (int f = 0; f < n; ++f) {
+      while (true) {
+        unsigned int v;
+        asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(flags + f) : "memory");
+        if (v >= value) break;
+        __nanosleep(200);
+        if ((++spins & 0xffu) == 0) {
+          const uint64_t now = globaltimer_ns();
+          if (t0 == 0) t0 = now;
+          if (now - t0 > timeout_ns) {
+            if (dbg != nullptr) {
+              dbg->block = blockIdx.x;
+              dbg->thread = static_cast<unsigned int>(f);
+              dbg->aux0 = v;
+              dbg->aux1 = value;
+              dbg->code = site;
+              __threadfence_system();
+            }
+            __trap();
           }
-          __trap();
         }
       }
     }
-    __threadfence();  // order the peer data reads of the other 63 threads after the observed flag
+    __threadfence();  // order the peer data reads of the other 63 threads after the observed flags
   }
   asm volatile("bar.sync 2, 64;" ::: "memory");
+}
+
+// Every CTA has finished its share of something: the last one to arrive (ticket) publishes. Called by ONE thread per
+// CTA after a barrier that covers the CTA's writers; returns true on the last CTA. The ticket is left at zero.
+__device__ __forceinline__ bool last_cta_arrives(unsigned int* ticket) {
+  __threadfence_system();                     // this CTA's writes (possibly read by peers over NVLink) before the ticket
+  const unsigned int t = atomicAdd(ticket, 1u);
+  if (t != gridDim.x - 1) return false;
+  atomicExch(ticket, 0u);                     // ready for the next launch
+  __threadfence_system();                     // the other CTAs' writes (observed through the ticket) before the signal
+  return true;
+}
+
+__device__ __forceinline__ void release_store_sys(unsigned int* flag, unsigned int value) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(flag), "r"(value) : "memory");
 }
 
 // 16-byte load of peer (NVLink-mapped) or streaming data: no L1 allocation, data is touched once
@@ -662,6 +681,7 @@ siglip_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_consta
     const long long epi_start = clock_cycles();
     int as = 0;
     uint32_t aphase = 0;
+    bool p1_ready = false;
     uint32_t empty_remote[kAccStages];
 #pragma unroll
     for (int a = 0; a < kAccStages; ++a) {
@@ -694,6 +714,37 @@ siglip_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_consta
       } else {
         scale = t_exact * p.inv_b * (p.grad_out != nullptr ? *p.grad_out : 1.0f);
         fix = (pr.fix_vec != nullptr && row < pr.M) ? pr.fix_vec[row] : 0.f;
+        if (tc.prob == 1 && p.p1_wait_flag != nullptr && !p1_ready) {
+          // the dtxt tiles of the LAST gradient launch add the folded sum of the peers' contributions: the fold that
+          // completes it runs in this very launch (auxiliary warps of all CTAs) and must have finished everywhere
+          if (lane == 0) {
+            uint64_t t0 = 0;
+            uint32_t spins = 0;
+            while (true) {
+              unsigned int v;
+              asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p.p1_wait_flag) : "memory");
+              if (v >= p.p1_wait_value) break;
+              __nanosleep(500);
+              if ((++spins & 0xffu) == 0) {
+                const uint64_t now = globaltimer_ns();
+                if (t0 == 0) t0 = now;
+                if (now - t0 > p.peer_timeout_ns) {
+                  if (p.dbg != nullptr) {
+                    p.dbg->block = blockIdx.x;
+                    p.dbg->thread = threadIdx.x;
+                    p.dbg->aux0 = v;
+                    p.dbg->aux1 = p.p1_wait_value;
+                    p.dbg->code = 8;
+                    __threadfence_system();
+                  }
+                  __trap();
+                }
+              }
+            }
+          }
+          __syncwarp();
+          p1_ready = true;
+        }
       }
 
       auto slab = [&](const uint32_t(&v)[32], int c) {
@@ -830,83 +881,99 @@ siglip_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_consta
     }
   } else {
     // ===================== the two auxiliary warps: NVSwitch peer pull, conversions, fold =====================
-    // The next text chunk is read ONCE from its owner's buffer (P2P over NVLink) into local HBM while this
-    // chunk's tiles compute (replaces distributed_utils.py:10-27 neighbour_exchange / the all_gather at
-    // distributed_sigmoid_loss.py:35). MMA operands are then fed from local memory only.
-    if (p.pull_bytes != 0) {
-      if (p.pull_wait_flag != nullptr) wait_peer_flag(p.pull_wait_flag, p.pull_wait_value, p.dbg, 5);
-      const unsigned long long n16 = p.pull_bytes >> 4;
-      const unsigned long long nthreads = static_cast<unsigned long long>(gridDim.x) * 64ull;
-      unsigned long long i = static_cast<unsigned long long>(blockIdx.x) * 64ull + (threadIdx.x - kAllocWarp * 32);
-      // 8 independent 16-byte peer loads in flight per thread (~1.2 MB per GPU) to cover the NVLink round trip
-      for (; i + 7ull * nthreads < n16; i += 8ull * nthreads) {
-        uint4 v[8];
-#pragma unroll
-        for (int u = 0; u < 8; ++u) v[u] = ld_peer_16(p.pull_src + i + u * nthreads);
-#pragma unroll
-        for (int u = 0; u < 8; ++u) p.pull_dst[i + u * nthreads] = v[u];
-      }
-      for (; i < n16; i += nthreads) p.pull_dst[i] = ld_peer_16(p.pull_src + i);
-    }
-    // bf16 -> scaled fp16 copies of the embeddings for the gradient kernel (its sigma operand is fp16, and an
-    // MMA cannot mix fp16 with bf16): done here, off the critical path, while the tiles of this chunk compute.
+    // A text chunk is read ONCE from its owner's buffer (P2P over NVLink) into local HBM while the previous chunk's
+    // tiles compute (replaces distributed_utils.py:10-27 neighbour_exchange / the all_gather at
+    // distributed_sigmoid_loss.py:35); MMA operands are then fed from local memory only. The peers' dtxt
+    // contributions are folded into a local fp32 accumulator the same way (the reduce-scatter of all_gather's backward,
+    // torch functional.py:343-354, spread over the steps instead of exposed at the end). Buffer hand-over between the
+    // ranks is by flags: waits before a job, release-stores once every CTA has finished its share of it.
+    const int aux_tid = static_cast<int>(threadIdx.x) - kAllocWarp * 32;
+    const unsigned long long nthreads = static_cast<unsigned long long>(gridDim.x) * 64ull;
+    const unsigned long long tid0 = static_cast<unsigned long long>(blockIdx.x) * 64ull + aux_tid;
+    const bool tracer = (p.aux_trace != nullptr && blockIdx.x == 0 && aux_tid == 0);
+    if (tracer) p.aux_trace[0] = globaltimer_ns();
+    unsigned long long waited_until = 0;
 #pragma unroll 1
-    for (int job = 0; job < 2; ++job) {
-      const uint4* src = p.cvt_src[job];
-      uint4* dst = p.cvt_dst[job];
-      const unsigned long long n16 = p.cvt_n16[job];
-      if (src == nullptr || n16 == 0) continue;
-      const float sc = p.cvt_scale;
-      const unsigned long long nthreads = static_cast<unsigned long long>(gridDim.x) * 64ull;
-      for (unsigned long long i = static_cast<unsigned long long>(blockIdx.x) * 64ull + (threadIdx.x - kAllocWarp * 32);
-           i < n16; i += nthreads) {
-        const uint4 v = src[i];
-        if (p.cvt_copy) {
-          dst[i] = v;
-          continue;
-        }
-        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
-        uint32_t o[4];
+    for (int j = 0; j < p.naux; ++j) {
+      const AuxJob& job = p.aux[j];
+      if (job.kind == kAuxNone) continue;
+      if (job.wait_flags != nullptr) {
+        wait_peer_flags(job.wait_flags, job.wait_n, job.wait_value, p.peer_timeout_ns, p.dbg, job.site);
+        if (tracer) waited_until = globaltimer_ns();
+      }
+      const unsigned long long n16 = job.n16;
+      if (job.kind == kAuxCopy) {
+        // 8 independent 16-byte loads in flight per thread (~1.2 MB per GPU) to cover the NVLink round trip
+        unsigned long long i = tid0;
+        for (; i + 7ull * nthreads < n16; i += 8ull * nthreads) {
+          uint4 v[8];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const float lo = fminf(fmaxf(__uint_as_float(w[q] << 16) * sc, -65504.f), 65504.f);
-          const float hi = fminf(fmaxf(__uint_as_float(w[q] & 0xffff0000u) * sc, -65504.f), 65504.f);
-          o[q] = pack_16x2<true>(lo, hi);
+          for (int u = 0; u < 8; ++u) v[u] = ld_peer_16(job.src + i + u * nthreads);
+#pragma unroll
+          for (int u = 0; u < 8; ++u) job.dst[i + u * nthreads] = v[u];
         }
-        dst[i] = make_uint4(o[0], o[1], o[2], o[3]);
+        for (; i < n16; i += nthreads) job.dst[i] = ld_peer_16(job.src + i);
+      } else if (job.kind == kAuxCvt) {
+        // bf16 -> scaled fp16 copies of the embeddings for the gradient kernel (its sigma operand is fp16, and an
+        // MMA cannot mix fp16 with bf16): done here, off the critical path, while the tiles of this chunk compute.
+        const float sc = p.cvt_scale;
+        for (unsigned long long i = tid0; i < n16; i += nthreads) {
+          const uint4 v = job.src[i];
+          if (job.cvt_copy) {
+            job.dst[i] = v;
+            continue;
+          }
+          const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+          uint32_t o[4];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const float lo = fminf(fmaxf(__uint_as_float(w[q] << 16) * sc, -65504.f), 65504.f);
+            const float hi = fminf(fmaxf(__uint_as_float(w[q] & 0xffff0000u) * sc, -65504.f), 65504.f);
+            o[q] = pack_16x2<true>(lo, hi);
+          }
+          job.dst[i] = make_uint4(o[0], o[1], o[2], o[3]);
+        }
+      } else if (job.kind == kAuxFold) {
+        const bool has_in = job.src2 != nullptr;   // first contribution of a backward pass: plain copy
+        const float4* acc_in = reinterpret_cast<const float4*>(job.src2);
+        float4* acc_out = reinterpret_cast<float4*>(job.dst);
+        unsigned long long i = tid0;
+        for (; i + 7ull * nthreads < n16; i += 8ull * nthreads) {
+          uint4 rv[8];
+#pragma unroll
+          for (int u = 0; u < 8; ++u) rv[u] = ld_peer_16(job.src + i + u * nthreads);
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            float4 a = has_in ? acc_in[i + u * nthreads] : make_float4(0.f, 0.f, 0.f, 0.f);
+            a.x += __uint_as_float(rv[u].x);
+            a.y += __uint_as_float(rv[u].y);
+            a.z += __uint_as_float(rv[u].z);
+            a.w += __uint_as_float(rv[u].w);
+            acc_out[i + u * nthreads] = a;
+          }
+        }
+        for (; i < n16; i += nthreads) {
+          const uint4 rr = ld_peer_16(job.src + i);
+          float4 a = has_in ? acc_in[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+          a.x += __uint_as_float(rr.x);
+          a.y += __uint_as_float(rr.y);
+          a.z += __uint_as_float(rr.z);
+          a.w += __uint_as_float(rr.w);
+          acc_out[i] = a;
+        }
+      }
+      if (job.ticket != nullptr) {
+        asm volatile("bar.sync 2, 64;" ::: "memory");      // this CTA's share is written
+        if (aux_tid == 0 && last_cta_arrives(job.ticket)) {
+          for (int i = 0; i < job.sig_n; ++i) release_store_sys(job.sig_ptrs[i], job.sig_value);
+          if (job.done_flag != nullptr)
+            asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(job.done_flag), "r"(job.done_value) : "memory");
+        }
       }
     }
-    // Progressive cross-rank reduction of the text gradient: while this chunk's tiles compute, add the contribution
-    // a peer finished one step ago (read over NVSwitch P2P) into the local fp32 accumulator. This is the reduce-scatter
-    // of all_gather's backward (torch functional.py:343-354), spread over the steps instead of exposed at the end.
-    if (p.acc_n4 != 0) {
-      if (p.acc_wait_flag != nullptr) wait_peer_flag(p.acc_wait_flag, p.acc_wait_value, p.dbg, 7);
-      const unsigned long long nthreads = static_cast<unsigned long long>(gridDim.x) * 64ull;
-      unsigned long long i = static_cast<unsigned long long>(blockIdx.x) * 64ull + (threadIdx.x - kAllocWarp * 32);
-      const bool has_in = p.acc_in != nullptr;   // first contribution of a backward pass: plain copy
-      for (; i + 7ull * nthreads < p.acc_n4; i += 8ull * nthreads) {
-        uint4 rv[8];
-#pragma unroll
-        for (int u = 0; u < 8; ++u) rv[u] = ld_peer_16(reinterpret_cast<const uint4*>(p.acc_remote) + i + u * nthreads);
-#pragma unroll
-        for (int u = 0; u < 8; ++u) {
-          float4 a = has_in ? p.acc_in[i + u * nthreads] : make_float4(0.f, 0.f, 0.f, 0.f);
-          a.x += __uint_as_float(rv[u].x);
-          a.y += __uint_as_float(rv[u].y);
-          a.z += __uint_as_float(rv[u].z);
-          a.w += __uint_as_float(rv[u].w);
-          p.acc_out[i + u * nthreads] = a;
-        }
-      }
-      for (; i < p.acc_n4; i += nthreads) {
-        const uint4 rr = ld_peer_16(reinterpret_cast<const uint4*>(p.acc_remote) + i);
-        float4 a = has_in ? p.acc_in[i] : make_float4(0.f, 0.f, 0.f, 0.f);
-        a.x += __uint_as_float(rr.x);
-        a.y += __uint_as_float(rr.y);
-        a.z += __uint_as_float(rr.z);
-        a.w += __uint_as_float(rr.w);
-        p.acc_out[i] = a;
-      }
+    if (tracer) {
+      p.aux_trace[1] = waited_until;
+      p.aux_trace[2] = globaltimer_ns();
     }
   }
 
@@ -920,6 +987,13 @@ siglip_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_consta
   if (warp == kAllocWarp) {
     tc_fence_after();
     tmem_dealloc<kCG>(tmem_base, kTmemCols);
+  }
+  // every warp of this CTA is past its last global write (barrier above): the last CTA of the launch tells the peers
+  if (threadIdx.x == 0 && p.end_ticket != nullptr) {
+    if (last_cta_arrives(p.end_ticket)) {
+      for (int i = 0; i < p.end_sig_n; ++i) release_store_sys(p.end_sig_ptrs[i], p.end_sig_value);
+      if (p.aux_trace != nullptr) p.aux_trace[3] = globaltimer_ns();
+    }
   }
 }
 
@@ -946,26 +1020,39 @@ __global__ void reduce_slots_kernel(void* __restrict__ out, int out_bf16, const 
   }
 }
 
-// dst = src * (*g): the whole backward() of the module (the gradients were produced for an upstream gradient of 1)
+// dst = src * (*g): the whole backward() of the module when the fused step already produced the gradients for an
+// upstream gradient of 1. 16-byte vectors when both buffers are 16-byte aligned, element-wise head / tail otherwise.
+__device__ __forceinline__ uint4 scale_vec(uint4 v, int is_bf16, float s) {
+  if (is_bf16) {
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+    uint32_t r[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+      r[q] = pack_16x2<false>(__uint_as_float(w[q] << 16) * s, __uint_as_float(w[q] & 0xffff0000u) * s);
+    return make_uint4(r[0], r[1], r[2], r[3]);
+  }
+  return make_uint4(__float_as_uint(__uint_as_float(v.x) * s), __float_as_uint(__uint_as_float(v.y) * s),
+                    __float_as_uint(__uint_as_float(v.z) * s), __float_as_uint(__uint_as_float(v.w) * s));
+}
+
 __global__ void scale_kernel(const void* __restrict__ src, void* __restrict__ dst, int is_bf16,
-                             const float* __restrict__ g, size_t nvec) {
+                             const float* __restrict__ g, size_t nbytes, int aligned) {
   const float s = *g;
   const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
-  for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < nvec; i += stride) {
-    const uint4 v = reinterpret_cast<const uint4*>(src)[i];
-    uint4 o;
+  const size_t tid = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const size_t nvec = aligned ? nbytes / 16 : 0;
+  for (size_t i = tid; i < nvec; i += stride)
+    reinterpret_cast<uint4*>(dst)[i] = scale_vec(reinterpret_cast<const uint4*>(src)[i], is_bf16, s);
+  // elements the vector loop did not cover (everything for unaligned buffers, < 16 bytes otherwise)
+  const size_t esz = is_bf16 ? 2 : 4;
+  const size_t first = nvec * 16 / esz, nel = nbytes / esz;
+  for (size_t i = first + tid; i < nel; i += stride) {
     if (is_bf16) {
-      const uint32_t w[4] = {v.x, v.y, v.z, v.w};
-      uint32_t r[4];
-#pragma unroll
-      for (int q = 0; q < 4; ++q)
-        r[q] = pack_16x2<false>(__uint_as_float(w[q] << 16) * s, __uint_as_float(w[q] & 0xffff0000u) * s);
-      o = make_uint4(r[0], r[1], r[2], r[3]);
+      const __nv_bfloat16 x = reinterpret_cast<const __nv_bfloat16*>(src)[i];
+      reinterpret_cast<__nv_bfloat16*>(dst)[i] = __float2bfloat16_rn(__bfloat162float(x) * s);
     } else {
-      o = make_uint4(__float_as_uint(__uint_as_float(v.x) * s), __float_as_uint(__uint_as_float(v.y) * s),
-                     __float_as_uint(__uint_as_float(v.z) * s), __float_as_uint(__uint_as_float(v.w) * s));
+      reinterpret_cast<float*>(dst)[i] = reinterpret_cast<const float*>(src)[i] * s;
     }
-    reinterpret_cast<uint4*>(dst)[i] = o;
   }
 }
 
@@ -978,7 +1065,8 @@ __global__ void signal_flags_kernel(unsigned int* const* flag_ptrs, int n, unsig
   }
 }
 
-__global__ void wait_flags_kernel(const volatile unsigned int* flags, int n, unsigned int value, DebugRecord* dbg) {
+__global__ void wait_flags_kernel(const volatile unsigned int* flags, int n, unsigned int value,
+                                  unsigned long long timeout_ns, DebugRecord* dbg) {
   const int i = threadIdx.x;
   if (i < n) {
     uint64_t t0 = 0;
@@ -990,7 +1078,7 @@ __global__ void wait_flags_kernel(const volatile unsigned int* flags, int n, uns
       if ((++spins & 0xffu) == 0) {
         const uint64_t now = globaltimer_ns();
         if (t0 == 0) t0 = now;
-        if (now - t0 > 20000000000ull) {
+        if (now - t0 > timeout_ns) {
           if (dbg != nullptr) {
             dbg->block = i;
             dbg->aux0 = v;
@@ -1013,7 +1101,8 @@ __global__ void allreduce_scalars_kernel(const float* __restrict__ saved, const 
                                          float* mailbox_local, const float* const* __restrict__ mailboxes,
                                          unsigned int* const* __restrict__ signal_ptrs,
                                          const volatile unsigned int* flags_local, int world, unsigned int value,
-                                         float* dt_prime, float* dbias, DebugRecord* dbg) {
+                                         float* dt_prime, float* dbias, unsigned long long timeout_ns,
+                                         DebugRecord* dbg) {
   __shared__ float sh[2][32];
   const int i = threadIdx.x;
   const float s = (g != nullptr) ? *g : 1.0f;
@@ -1034,12 +1123,12 @@ __global__ void allreduce_scalars_kernel(const float* __restrict__ saved, const 
       if ((++spins & 0xffu) == 0) {
         const uint64_t now = globaltimer_ns();
         if (t0 == 0) t0 = now;
-        if (now - t0 > 20000000000ull) {
+        if (now - t0 > timeout_ns) {
           if (dbg != nullptr) {
             dbg->block = i;
             dbg->aux0 = v;
             dbg->aux1 = value;
-            dbg->code = 7;
+            dbg->code = 9;
             __threadfence_system();
           }
           __trap();
@@ -1366,16 +1455,17 @@ int launch_normalize_bwd(const void* x, int in_bf16, const float* inv_norm, cons
 
 int launch_scale(const void* src, void* dst, int is_bf16, const float* g, size_t nbytes, int num_sms,
                  cudaStream_t stream) {
-  scale_kernel<<<num_sms * 4, 256, 0, stream>>>(src, dst, is_bf16, g, nbytes / 16);
+  const int aligned = ((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst)) & 15u) == 0;
+  scale_kernel<<<num_sms * 4, 256, 0, stream>>>(src, dst, is_bf16, g, nbytes, aligned);
   return static_cast<int>(cudaGetLastError());
 }
 
 int launch_allreduce_scalars(const float* saved, const float* g, float* mailbox_local, const float* const* mailboxes_dev,
                              unsigned int* const* signal_ptrs_dev, const volatile unsigned int* flags_local, int world,
-                             unsigned int value, float* dt_prime, float* dbias, DebugRecord* dbg,
-                             cudaStream_t stream) {
+                             unsigned int value, float* dt_prime, float* dbias, unsigned long long timeout_ns,
+                             DebugRecord* dbg, cudaStream_t stream) {
   allreduce_scalars_kernel<<<1, 32, 0, stream>>>(saved, g, mailbox_local, mailboxes_dev, signal_ptrs_dev, flags_local,
-                                                 world, value, dt_prime, dbias, dbg);
+                                                 world, value, dt_prime, dbias, timeout_ns, dbg);
   return static_cast<int>(cudaGetLastError());
 }
 
@@ -1384,9 +1474,9 @@ int launch_signal_flags(unsigned int* const* flag_ptrs_dev, int n, unsigned int 
   return static_cast<int>(cudaGetLastError());
 }
 
-int launch_wait_flags(const volatile unsigned int* flags, int n, unsigned int value, DebugRecord* dbg,
-                      cudaStream_t stream) {
-  wait_flags_kernel<<<1, 32, 0, stream>>>(flags, n, value, dbg);
+int launch_wait_flags(const volatile unsigned int* flags, int n, unsigned int value, unsigned long long timeout_ns,
+                      DebugRecord* dbg, cudaStream_t stream) {
+  wait_flags_kernel<<<1, 32, 0, stream>>>(flags, n, value, timeout_ns, dbg);
   return static_cast<int>(cudaGetLastError());
 }
 

@@ -34,6 +34,31 @@ struct Problem {
   long long ld_add;
 };
 
+constexpr int kMaxAuxJobs = 6;
+enum AuxKind { kAuxNone = 0, kAuxCopy = 1, kAuxCvt = 2, kAuxFold = 3, kAuxWaitOnly = 4 };
+
+// One job of the auxiliary warps. Optional pre-wait on `wait_n` consecutive local flags (all >= wait_value, written by
+// peers with st.release.sys), then the data movement, then — once EVERY CTA has finished its share (ticket) — an
+// optional release-store of sig_value to sig_n peer flags and / or of done_value to a local flag.
+struct AuxJob {
+  int kind;
+  const volatile unsigned int* wait_flags;  // null = no wait
+  int wait_n;
+  unsigned int wait_value;
+  unsigned int site;          // id reported if the wait times out
+  const uint4* src;           // kAuxCopy / kAuxCvt: source (may be peer memory); kAuxFold: remote fp32 contribution
+  const uint4* src2;          // kAuxFold: local fp32 accumulator input (null = 0)
+  uint4* dst;
+  unsigned long long n16;     // 16-byte vectors
+  int cvt_copy;               // kAuxCvt: 1 = plain copy (sources already fp16)
+  unsigned int* const* sig_ptrs;
+  int sig_n;
+  unsigned int sig_value;
+  unsigned int* done_flag;    // local flag (gpu scope) set to done_value when the job is complete on every CTA
+  unsigned int done_value;
+  unsigned int* ticket;       // zero between launches; required when sig_n > 0 or done_flag != null
+};
+
 struct KernelParams {
   Problem prob[2];
   int nprob;
@@ -65,27 +90,23 @@ struct KernelParams {
   DebugRecord* dbg;
   unsigned long long* wait_stats;  // optional [gridDim.x][4]: producer empty-wait, MMA full-wait, MMA tmem-wait, MMA loop cycles
   unsigned int epi_sleep_ns;  // back-off of the epilogue warps while they wait for an accumulator (0 = spin)
-  // optional NVSwitch peer pull performed by otherwise idle warps while the tiles compute:
-  // copy `pull_bytes` from pull_src (peer GPU memory, P2P mapped) to pull_dst (local), both 16-B aligned.
-  const uint4* pull_src;
-  uint4* pull_dst;
-  unsigned long long pull_bytes;
-  // flag the pull must see (>= pull_wait_value) before reading the peer buffer; null = no wait
-  const volatile unsigned int* pull_wait_flag;
-  unsigned int pull_wait_value;
-  // optional bf16 -> fp16 (x cvt_scale, clamped) conversions done by the same idle warps: [n16] 16-byte vectors each
-  const uint4* cvt_src[2];
-  uint4* cvt_dst[2];
-  unsigned long long cvt_n16[2];
-  float cvt_scale;
-  int cvt_copy;   // 1: the sources already are fp16 x cvt_scale (fp32-input path): plain copies
-  // optional fp32 accumulate job of the same warps: acc_out = acc_in + acc_remote (acc_remote may be peer memory)
-  const float4* acc_in;
-  const float4* acc_remote;
-  float4* acc_out;
-  unsigned long long acc_n4;
-  const volatile unsigned int* acc_wait_flag;
-  unsigned int acc_wait_value;
+  // Work of the two auxiliary warps of every CTA while the tiles compute: up to kMaxAuxJobs jobs executed in order,
+  // each spread over all CTAs of the launch (grid-stride over 16-byte vectors). This is where the cross-rank exchange
+  // lives: peer pulls of text chunks and folds of the peers' dtxt contributions over NVSwitch P2P, ordered by flags.
+  AuxJob aux[kMaxAuxJobs];
+  int naux;
+  float cvt_scale;   // kAuxCvt: dst = fp16(src_bf16 * cvt_scale), clamped
+  // Signal written when the LAST CTA of the launch has finished (ticket counter): everything this launch wrote is then
+  // visible to the peers that observe the flag (st.release.sys after a system-scope fence).
+  unsigned int* const* end_sig_ptrs;   // device array of flag addresses (peer-mapped), null = no signal
+  int end_sig_n;
+  unsigned int end_sig_value;
+  unsigned int* end_ticket;
+  // out kernel, problem 1: do not read add_src before this local flag (set by an aux job's done_flag) holds done_value
+  const volatile unsigned int* p1_wait_flag;
+  unsigned int p1_wait_value;
+  unsigned long long peer_timeout_ns;  // bound of every wait on a peer flag (a dead peer traps instead of hanging)
+  unsigned long long* aux_trace;       // optional [4] globaltimer stamps of CTA 0's aux thread: start, flags seen, jobs done
 };
 
 enum KernelMode { kModeLoss = 0, kModeOut = 1 };
@@ -125,9 +146,10 @@ int launch_scale(const void* src, void* dst, int is_bf16, const float* g, size_t
 // cross-rank flag helpers (peer-mapped pointers)
 int launch_allreduce_scalars(const float* saved, const float* g, float* mailbox_local, const float* const* mailboxes_dev,
                              unsigned int* const* signal_ptrs_dev, const volatile unsigned int* flags_local, int world,
-                             unsigned int value, float* dt_prime, float* dbias, DebugRecord* dbg, cudaStream_t stream);
+                             unsigned int value, float* dt_prime, float* dbias, unsigned long long timeout_ns,
+                             DebugRecord* dbg, cudaStream_t stream);
 int launch_signal_flags(unsigned int* const* flag_ptrs_dev, int n, unsigned int value, cudaStream_t stream);
-int launch_wait_flags(const volatile unsigned int* flags, int n, unsigned int value, DebugRecord* dbg,
-                      cudaStream_t stream);
+int launch_wait_flags(const volatile unsigned int* flags, int n, unsigned int value, unsigned long long timeout_ns,
+                      DebugRecord* dbg, cudaStream_t stream);
 
 }  // namespace siglip

@@ -47,15 +47,27 @@ class SigmoidLossEngine:
     """Owns one ``siglip_ctx`` (workspaces + peer mappings) for a fixed (device, B, D, process group)."""
 
     def __init__(self, batch: int, dim: int, device: torch.device, group=None, cta_group: int = 2,
-                 overlap_pull: bool = True, rank_world: Optional[Tuple[int, int]] = None, loopback: bool = False):
+                 overlap_pull: bool = True, rank_world: Optional[Tuple[int, int]] = None, loopback: bool = False,
+                 batch_per_rank=None):
         self._L = _capi.lib()
         if not torch.cuda.is_available() or self._L.siglip_device_count() == 0:
             raise RuntimeError("distributed_sigmoid_loss_b200 needs an sm_100 (B200) device; there is no CPU fallback")
         self.batch, self.dim, self.device, self.group = batch, dim, torch.device(device), group
         self.rank, self.world = rank_world if rank_world is not None else _group_rank_world(group)
         h = ctypes.c_void_p()
-        _capi.check(self._L.siglip_ctx_create(ctypes.byref(h), self.device.index or 0, self.rank, self.world,
-                                              batch, dim))
+        if batch_per_rank is not None:
+            # extension (SURVEY.md §8f-4): ranks with different batch sizes; every rank passes the same list
+            bpr = [int(b) for b in batch_per_rank]
+            if len(bpr) != self.world or bpr[self.rank] != batch:
+                raise RuntimeError(f"batch_per_rank {bpr} must list one batch per rank and hold {batch} at rank {self.rank}")
+            arr = (ctypes.c_int * self.world)(*bpr)
+            _capi.check(self._L.siglip_ctx_create_uneven(ctypes.byref(h), self.device.index or 0, self.rank, self.world,
+                                                         arr, dim))
+            self.batch_per_rank = bpr
+        else:
+            _capi.check(self._L.siglip_ctx_create(ctypes.byref(h), self.device.index or 0, self.rank, self.world,
+                                                  batch, dim))
+            self.batch_per_rank = [batch] * self.world
         self._h = h
         _capi.check(self._L.siglip_ctx_set_option(h, _capi.SIGLIP_OPT_CTA_GROUP, int(cta_group)))
         _capi.check(self._L.siglip_ctx_set_option(h, _capi.SIGLIP_OPT_OVERLAP_PULL, int(bool(overlap_pull))))
@@ -91,9 +103,21 @@ class SigmoidLossEngine:
         _capi.check(self._L.siglip_debug_set_text_chunk(self._h, chunk, txt.data_ptr(), self._stream()))
 
     def debug_get_slot(self, chunk: int) -> torch.Tensor:
-        out = torch.empty(self.batch, self.dim, device=self.device, dtype=torch.float32)
+        out = torch.empty(self.batch_per_rank[chunk], self.dim, device=self.device, dtype=torch.float32)
         _capi.check(self._L.siglip_debug_get_slot(self._h, chunk, out.data_ptr(), self._stream()))
         return out
+
+    def debug_set_mailbox(self, peer: int, dt_prime: float, dbias: float) -> None:
+        _capi.check(self._L.siglip_debug_set_mailbox(self._h, peer, float(dt_prime), float(dbias)))
+
+    def aux_trace(self, max_launches: int = 4096):
+        """[(start, flags_seen, jobs_done, launch_end)] globaltimer ns per launch since the last call; needs
+        SIGLIP_OPT_AUX_TRACE."""
+        buf = (ctypes.c_ulonglong * (4 * max_launches))()
+        n = ctypes.c_int(0)
+        _capi.check(self._L.siglip_ctx_aux_trace(self._h, ctypes.cast(buf, ctypes.c_void_p), max_launches,
+                                                 ctypes.byref(n)))
+        return [tuple(int(buf[4 * i + j]) for j in range(4)) for i in range(n.value)]
 
     @property
     def workspace_bytes(self) -> int:
@@ -107,10 +131,12 @@ class SigmoidLossEngine:
         return torch.cuda.current_stream(self.device).cuda_stream
 
     def fwd_bwd(self, img: torch.Tensor, txt: torch.Tensor, t_prime: torch.Tensor, bias: torch.Tensor,
-                grad_dtype: torch.dtype = torch.float32):
-        """img/txt: [B, D] bf16 contiguous on self.device; t_prime/bias: fp32 [1]. Returns
-        (loss[1], dimg[B,D], dtxt[B,D], dt_prime[1], dbias[1]) for an upstream gradient of 1; scalars are fp32,
-        dimg/dtxt are `grad_dtype` (fp32, or bf16 written directly by the kernel epilogue)."""
+                grad_dtype: torch.dtype = torch.float32, grad_out: Optional[torch.Tensor] = None):
+        """The fused step (siglip_fwd_bwd): loss and gradient kernels alternate chunk by chunk, two sigma operands
+        whatever the world size. img/txt: [B, D] bf16 contiguous on self.device; t_prime/bias: fp32 [1]. Returns
+        (loss[1], dimg[B,D], dtxt[B,D], dt_prime[1], dbias[1]) for an upstream gradient of 1 (or `grad_out`, a
+        1-element fp32 device tensor, multiplied in by the kernel epilogues); scalars are fp32, dimg/dtxt are
+        `grad_dtype` (fp32, or bf16 written directly by the kernel epilogue)."""
         self._check(img, txt)
         self._set_grad_dtype(grad_dtype)
         opts = dict(device=self.device, dtype=torch.float32)
@@ -119,9 +145,10 @@ class SigmoidLossEngine:
         dimg = torch.empty(self.batch, self.dim, device=self.device, dtype=grad_dtype)
         dtxt = torch.empty(self.batch, self.dim, device=self.device, dtype=grad_dtype)
         with torch.cuda.device(self.device):
-            _capi.check(self._L.siglip_fwd_bwd(self._h, img.data_ptr(), txt.data_ptr(), t_prime.data_ptr(),
-                                               bias.data_ptr(), loss.data_ptr(), dimg.data_ptr(), dtxt.data_ptr(),
-                                               dtp.data_ptr(), db.data_ptr(), self._stream()))
+            _capi.check(self._L.siglip_fwd_bwd_scaled(
+                self._h, img.data_ptr(), txt.data_ptr(), t_prime.data_ptr(), bias.data_ptr(),
+                grad_out.data_ptr() if grad_out is not None else None, loss.data_ptr(), dimg.data_ptr(),
+                dtxt.data_ptr(), dtp.data_ptr(), db.data_ptr(), self._stream()))
         return loss, dimg, dtxt, dtp, db
 
     # -- the two halves autograd uses ----------------------------------------------------------------------
@@ -190,11 +217,11 @@ class SigmoidLossEngine:
 
     def scale(self, src: torch.Tensor, g: torch.Tensor) -> torch.Tensor:
         """src * g with g a 1-element fp32 device tensor (grad_output): one fused pass of the C library."""
-        if src.dtype not in (torch.float32, torch.bfloat16) or not src.is_contiguous():
-            return src * g.to(src.dtype)
+        if src.dtype not in (torch.float32, torch.bfloat16) or src.device != self.device:
+            raise RuntimeError("scale expects an fp32 or bf16 tensor on the engine's device")
+        if not src.is_contiguous():
+            src = src.contiguous()
         nbytes = src.numel() * src.element_size()
-        if nbytes % 16 != 0:
-            return src * g.to(src.dtype)
         dst = torch.empty_like(src)
         with torch.cuda.device(self.device):
             _capi.check(self._L.siglip_scale(self._h, src.data_ptr(), dst.data_ptr(), nbytes,
@@ -224,15 +251,24 @@ class SigmoidLossEngine:
                 loss_p + 4, loss_p + 8, self._stream()))
         return float(out[0]), float(out[1]), float(out[2])
 
-    def host_submit(self, img_host: torch.Tensor, txt_host: torch.Tensor, t_prime: float, bias: float) -> int:
+    def host_submit(self, img_host: torch.Tensor, txt_host: torch.Tensor, t_prime: float, bias: float,
+                    dimg_host: Optional[torch.Tensor] = None, dtxt_host: Optional[torch.Tensor] = None) -> int:
         """Pipelined end-to-end step on HOST bf16 buffers: enqueue this step's host->device copies (internal copy
-        stream, two staging sets), the step and the device->host copy of its scalars; returns a ticket for
-        ``host_wait``. At most two steps in flight; the host tensors must stay alive until the ticket is waited."""
+        stream, two staging sets), the step and the device->host copy of its scalars — and, when `dimg_host` /
+        `dtxt_host` (CPU bf16 [B, D], pinned recommended) are given, of its bf16 gradients on a second copy stream;
+        returns a ticket for ``host_wait``. At most two steps in flight; the host tensors must stay alive until the
+        ticket is waited."""
         self._check_host(img_host, txt_host)
+        if (dimg_host is None) != (dtxt_host is None):
+            raise RuntimeError("give both gradient host buffers or neither")
+        if dimg_host is not None:
+            self._check_host(dimg_host, dtxt_host)
         ticket = ctypes.c_ulonglong(0)
         with torch.cuda.device(self.device):
-            _capi.check(self._L.siglip_host_submit(self._h, img_host.data_ptr(), txt_host.data_ptr(), float(t_prime),
-                                                   float(bias), ctypes.byref(ticket), self._stream()))
+            _capi.check(self._L.siglip_host_submit_grads(
+                self._h, img_host.data_ptr(), txt_host.data_ptr(), float(t_prime), float(bias),
+                dimg_host.data_ptr() if dimg_host is not None else None,
+                dtxt_host.data_ptr() if dtxt_host is not None else None, ctypes.byref(ticket), self._stream()))
         return int(ticket.value)
 
     def host_wait(self, ticket: int):
@@ -290,15 +326,27 @@ class SigmoidLossEngine:
             pass
 
 
+def _aligned(x: torch.Tensor) -> torch.Tensor:
+    """Contiguous and 16-byte aligned (TMA / 16-byte vector accesses): a view into the middle of a storage is cloned
+    instead of rejected."""
+    x = x.contiguous()
+    return x if x.data_ptr() % 16 == 0 else x.clone()
+
+
 class _SigmoidLossFn(torch.autograd.Function):
     """loss = sum_chunks(-logsigmoid(labels * (img @ txt_chunk.T * exp(t') + b))).sum() / B.
-    forward  = the loss kernels (the sigma operands stay in the engine when a gradient is needed),
-    backward = the gradient kernels, with grad_output folded into their epilogues (the four gradients
-    depend on the logits and a scalar only).
+
+    Two schedules, same kernels, same results (the four gradients depend on the logits and ONE upstream
+    scalar only):
+      * split  (fused=False): forward = the W loss kernels, the sigma operands of all W chunks stay in the engine;
+        backward = the W gradient kernels with grad_output folded into their epilogues. O(W B^2) workspace.
+      * fused  (fused=True): forward = the fused step (loss and gradient kernels alternating chunk by chunk, two sigma
+        operands, every cross-rank flag handled inside the kernels) which leaves the gradients for an upstream gradient
+        of 1; backward = one multiply by grad_output per tensor (siglip_scale). O(B^2) workspace.
     normalize=True additionally fuses F.normalize of both inputs (forward) and its backward around the loss."""
 
     @staticmethod
-    def forward(ctx, img, txt, t_prime, bias, engine: SigmoidLossEngine, normalize: bool = False):
+    def forward(ctx, img, txt, t_prime, bias, engine: SigmoidLossEngine, normalize: bool = False, fused: bool = False):
         need_grad = any(ctx.needs_input_grad[:4])
         raw = None
         # bf16 callers: bf16 operands (what autograd would multiply). Anything wider (the reference's own test feeds
@@ -310,28 +358,39 @@ class _SigmoidLossFn(torch.autograd.Function):
                 x = x.detach()
                 if x.dtype not in (torch.float32, torch.bfloat16):
                     x = x.float()
-                return x.contiguous()
+                return _aligned(x)
             img_r, txt_r = prep(img), prep(txt)
             img_b, inv_i = engine.normalize_fwd(img_r, hi)
             txt_b, inv_t = engine.normalize_fwd(txt_r, hi)
             raw = (img_r, txt_r, inv_i, inv_t)
         elif hi:
-            img_b = engine.convert_f32(img.detach().float().contiguous(), True)
-            txt_b = engine.convert_f32(txt.detach().float().contiguous(), True)
+            img_b = engine.convert_f32(_aligned(img.detach().float()), True)
+            txt_b = engine.convert_f32(_aligned(txt.detach().float()), True)
         else:
-            img_b = img.detach().contiguous()
-            txt_b = txt.detach().contiguous()
+            img_b = _aligned(img.detach())
+            txt_b = _aligned(txt.detach())
         tp = t_prime.detach().to(device=img.device, dtype=torch.float32).reshape(1)
         b = bias.detach().to(device=img.device, dtype=torch.float32).reshape(1)
-        loss = engine.forward(img_b, txt_b, tp, b, need_grad)
-        if need_grad:
+        ctx.fused = bool(fused and need_grad)
+        if ctx.fused:
+            # gradients in the dtype autograd would return for these inputs (fp32 when a projection follows)
+            gdt = torch.bfloat16 if (not hi and not normalize) else torch.float32
+            loss, dimg, dtxt, dtp, db = engine.fwd_bwd(img_b, txt_b, tp, b, gdt)
+            saved = [dimg, dtxt, dtp, db]
             if raw is not None:
-                ctx.save_for_backward(img_b, txt_b, tp, b, *raw)
-            else:
-                ctx.save_for_backward(img_b, txt_b, tp, b)
+                saved += list(raw)
+            ctx.save_for_backward(*saved)
+        else:
+            loss = engine.forward(img_b, txt_b, tp, b, need_grad)
+            if need_grad:
+                if raw is not None:
+                    ctx.save_for_backward(img_b, txt_b, tp, b, *raw)
+                else:
+                    ctx.save_for_backward(img_b, txt_b, tp, b)
+                ctx.gen = engine.saved_generation
+        if need_grad:
             ctx.normalize = normalize
             ctx.engine = engine
-            ctx.gen = engine.saved_generation
             ctx.in_meta = (img.dtype, txt.dtype, t_prime.dtype, bias.dtype, t_prime.shape, bias.shape,
                            t_prime.device, bias.device)
         # reference result dtype: promote(input dtype, fp32 labels) (distributed_sigmoid_loss.py:28-32)
@@ -341,37 +400,50 @@ class _SigmoidLossFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, grad_out):
         saved = ctx.saved_tensors
-        img_b, txt_b, tp, b = saved[:4]
         eng = ctx.engine
         idt, tdt, pdt, bdt, pshape, bshape, pdev, bdev = ctx.in_meta
-        if eng.saved_generation != ctx.gen:
-            # another forward of the same module ran in between: rebuild the saved state (every rank takes this branch
-            # together, so the collective stays matched)
-            eng.forward(img_b, txt_b, tp, b, True)
-            ctx.gen = eng.saved_generation
         g = grad_out.detach().to(torch.float32).reshape(1).contiguous()
-        if ctx.normalize:
-            # fp32 gradients w.r.t. the normalised embeddings, then the projection of F.normalize's backward
-            img_r, txt_r, inv_i, inv_t = saved[4:]
-            dimg, dtxt, dtp, db = eng.backward(img_b, txt_b, tp, g, torch.float32)
-            gi = eng.normalize_bwd(img_r, inv_i, dimg).to(idt) if ctx.needs_input_grad[0] else None
-            gt = eng.normalize_bwd(txt_r, inv_t, dtxt).to(tdt) if ctx.needs_input_grad[1] else None
+        if ctx.fused:
+            dimg, dtxt, dtp, db = saved[:4]
+            if ctx.normalize:
+                img_r, txt_r, inv_i, inv_t = saved[4:]
+                gi = eng.normalize_bwd(img_r, inv_i, eng.scale(dimg, g)).to(idt) if ctx.needs_input_grad[0] else None
+                gt = eng.normalize_bwd(txt_r, inv_t, eng.scale(dtxt, g)).to(tdt) if ctx.needs_input_grad[1] else None
+            else:
+                gi = eng.scale(dimg, g).to(idt) if ctx.needs_input_grad[0] else None
+                gt = eng.scale(dtxt, g).to(tdt) if ctx.needs_input_grad[1] else None
+            sc = eng.scale(torch.cat([dtp, db]), g)
+            dtp, db = sc[0:1], sc[1:2]
         else:
-            # gradients in the dtype autograd would return for these inputs: bf16 straight from the kernel epilogue
-            gdt = torch.bfloat16 if (idt == torch.bfloat16 and tdt == torch.bfloat16) else torch.float32
-            dimg, dtxt, dtp, db = eng.backward(img_b, txt_b, tp, g, gdt)
-            gi = dimg.to(idt) if ctx.needs_input_grad[0] else None
-            gt = dtxt.to(tdt) if ctx.needs_input_grad[1] else None
+            img_b, txt_b, tp, b = saved[:4]
+            if eng.saved_generation != ctx.gen:
+                # another forward of the same module ran in between: rebuild the saved state (every rank takes this
+                # branch together, so the collective stays matched)
+                eng.forward(img_b, txt_b, tp, b, True)
+                ctx.gen = eng.saved_generation
+            if ctx.normalize:
+                # fp32 gradients w.r.t. the normalised embeddings, then the projection of F.normalize's backward
+                img_r, txt_r, inv_i, inv_t = saved[4:]
+                dimg, dtxt, dtp, db = eng.backward(img_b, txt_b, tp, g, torch.float32)
+                gi = eng.normalize_bwd(img_r, inv_i, dimg).to(idt) if ctx.needs_input_grad[0] else None
+                gt = eng.normalize_bwd(txt_r, inv_t, dtxt).to(tdt) if ctx.needs_input_grad[1] else None
+            else:
+                # gradients in the dtype autograd would return for these inputs: bf16 straight from the kernel epilogue
+                gdt = torch.bfloat16 if (idt == torch.bfloat16 and tdt == torch.bfloat16) else torch.float32
+                dimg, dtxt, dtp, db = eng.backward(img_b, txt_b, tp, g, gdt)
+                gi = dimg.to(idt) if ctx.needs_input_grad[0] else None
+                gt = dtxt.to(tdt) if ctx.needs_input_grad[1] else None
         gp = dtp.reshape(pshape).to(device=pdev, dtype=pdt) if ctx.needs_input_grad[2] else None
         gb = db.reshape(bshape).to(device=bdev, dtype=bdt) if ctx.needs_input_grad[3] else None
-        return gi, gt, gp, gb, None, None
+        return gi, gt, gp, gb, None, None, None
 
 
 class _EngineCache:
     def __init__(self, group=None, cta_group: int = 2, overlap_pull: bool = True, sync_scalar_grads: bool = False,
-                 bidir: bool = False):
+                 bidir: bool = False, batch_per_rank=None):
         self.group, self.cta_group, self.overlap_pull = group, cta_group, overlap_pull
         self.sync_scalar_grads, self.bidir = sync_scalar_grads, bidir
+        self.batch_per_rank = batch_per_rank
         self._engines: Dict[Tuple[int, int, int], SigmoidLossEngine] = {}
 
     def get(self, batch: int, dim: int, device: torch.device) -> SigmoidLossEngine:
@@ -379,7 +451,8 @@ class _EngineCache:
         eng = self._engines.get(key)
         if eng is None:
             dev = torch.device("cuda", key[0])
-            eng = SigmoidLossEngine(batch, dim, dev, self.group, self.cta_group, self.overlap_pull)
+            eng = SigmoidLossEngine(batch, dim, dev, self.group, self.cta_group, self.overlap_pull,
+                                    batch_per_rank=self.batch_per_rank)
             if self.sync_scalar_grads:
                 eng.set_option(_capi.SIGLIP_OPT_SYNC_SCALAR_GRADS, 1)
             if self.bidir:
@@ -402,8 +475,13 @@ def _validate(image_embeddings: torch.Tensor, text_embeddings: torch.Tensor, exp
             "batch does not equal gpu_batch_size")
     if image_embeddings.device.type != "cuda" or text_embeddings.device != image_embeddings.device:
         raise RuntimeError("distributed_sigmoid_loss_b200 runs on CUDA (sm_100a) tensors only; there is no CPU path")
-    if image_embeddings.shape[1] % 8 != 0:
-        raise RuntimeError("emb_dim must be a multiple of 8 (16-byte rows for TMA)")
+
+
+def _pad_dim(x: torch.Tensor) -> torch.Tensor:
+    """Zero-pad the embedding dimension to a multiple of 8 (16-byte rows for TMA). Zero columns change no dot product;
+    F.pad is differentiable, so the gradient comes back sliced to the caller's width."""
+    d = x.shape[1]
+    return x if d % 8 == 0 else torch.nn.functional.pad(x, (0, 8 - d % 8))
 
 
 class DDPSigmoidLoss(nn.Module):
@@ -411,12 +489,20 @@ class DDPSigmoidLoss(nn.Module):
 
     ``t_prime`` (0-dim, float64 like ``torch.tensor(np.log(10))``) and ``bias`` (0-dim fp32, -10) are
     ``nn.Parameter``s with the reference's state_dict keys; hand them to the optimizer (README.md:20).
-    Embeddings are expected L2-normalised by the caller (distributed_sigmoid_loss.py:20).
+    Embeddings are expected L2-normalised by the caller (distributed_sigmoid_loss.py:20); with
+    ``normalize_inputs=False`` values must satisfy |x| <= 4094 (the gradient kernels consume fp16(16 x) copies;
+    unit-norm embeddings are six orders of magnitude inside that).
     Every rank of ``group`` must call ``forward`` the same number of times (collective, like all_gather).
+
+    Limits (also reported by the C library when violated): all ranks of ``group`` must be GPUs of ONE node with NVLink /
+    P2P access to each other (the exchange is CUDA-IPC peer memory, not NCCL), at most 32 ranks; give a multi-node job a
+    per-node ``group``. A rank waiting for a peer inside a kernel gives up after ``SIGLIP_PEER_TIMEOUT_MS`` (default
+    10 minutes).
     """
 
     def __init__(self, gpu_batch_size: int, group=None, cta_group: int = 2, overlap_pull: bool = True,
-                 normalize_inputs: bool = False, sync_scalar_grads: bool = False) -> None:
+                 normalize_inputs: bool = False, sync_scalar_grads: bool = False, fused_step: Optional[bool] = None,
+                 batch_per_rank=None) -> None:
         super().__init__()
         self.t_prime = nn.Parameter(torch.tensor(math.log(10), dtype=torch.float64))
         self.bias = nn.Parameter(torch.tensor(-10.0))
@@ -427,16 +513,22 @@ class DDPSigmoidLoss(nn.Module):
         # of the two parameters would give, README.md:20), so the module needs no DDP wrapper of its own. Collective:
         # every rank must set it, and every rank's backward must run.
         self.sync_scalar_grads = sync_scalar_grads
-        self._cache = _EngineCache(group, cta_group, overlap_pull, sync_scalar_grads)
+        # schedule: None = the fused step (two sigma operands, all flags in-kernel) when the group has more than one
+        # rank, the split forward / backward otherwise (one operand either way; saves the multiply by grad_output)
+        self.fused_step = fused_step
+        # extension: per-rank batch sizes may differ; every rank passes the same list
+        self._cache = _EngineCache(group, cta_group, overlap_pull, sync_scalar_grads, batch_per_rank=batch_per_rank)
 
     def engine_for(self, batch: int, dim: int, device: torch.device) -> SigmoidLossEngine:
-        return self._cache.get(batch, dim, device)
+        return self._cache.get(batch, (dim + 7) // 8 * 8, device)
 
     def forward(self, image_embeddings: torch.Tensor, text_embeddings: torch.Tensor) -> torch.Tensor:
         _validate(image_embeddings, text_embeddings, self.gpu_batch_size)
+        image_embeddings, text_embeddings = _pad_dim(image_embeddings), _pad_dim(text_embeddings)
         eng = self._cache.get(image_embeddings.shape[0], image_embeddings.shape[1], image_embeddings.device)
+        fused = (eng.world > 1) if self.fused_step is None else bool(self.fused_step)
         return _SigmoidLossFn.apply(image_embeddings, text_embeddings, self.t_prime, self.bias, eng,
-                                    self.normalize_inputs)
+                                    self.normalize_inputs, fused)
 
 
 SigmoidLoss = DDPSigmoidLoss
@@ -449,15 +541,17 @@ class SigLipLoss(nn.Module):
     ...; the pairs covered and the result are the same."""
 
     def __init__(self, cache_labels: bool = False, rank: int = 0, world_size: int = 1, bidir: bool = True,
-                 use_horovod: bool = False, group=None, cta_group: int = 2):
+                 use_horovod: bool = False, group=None, cta_group: int = 2, fused_step: Optional[bool] = None):
         super().__init__()
         assert not use_horovod  # same restriction as the reference (rwightman_sigmoid_loss.py:35)
         self.cache_labels, self.rank, self.world_size, self.bidir = cache_labels, rank, world_size, bidir
         self.use_horovod = use_horovod
+        self.fused_step = fused_step
         self._cache = _EngineCache(group, cta_group, bidir=bidir)
 
     def forward(self, image_features, text_features, logit_scale, logit_bias, output_dict: bool = False):
         _validate(image_features, text_features, None)
+        image_features, text_features = _pad_dim(image_features), _pad_dim(text_features)
         eng = self._cache.get(image_features.shape[0], image_features.shape[1], image_features.device)
         if (eng.rank, eng.world) != (self.rank, self.world_size):
             raise RuntimeError(
@@ -465,5 +559,6 @@ class SigLipLoss(nn.Module):
                 f"(rank={eng.rank}, world_size={eng.world})")
         if logit_bias is None:
             logit_bias = torch.zeros((), device=image_features.device)
-        loss = _SigmoidLossFn.apply(image_features, text_features, logit_scale, logit_bias, eng)
+        fused = (eng.world > 1) if self.fused_step is None else bool(self.fused_step)
+        loss = _SigmoidLossFn.apply(image_features, text_features, logit_scale, logit_bias, eng, False, fused)
         return {"contrastive_loss": loss} if output_dict else loss

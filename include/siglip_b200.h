@@ -65,7 +65,22 @@ enum {
                                 bf16: 11 significant bits for callers with fp32 embeddings (the reference's own test feeds fp32,
                                 test_distributed_sigmoid_loss.py:57-68; bf16 rounding of such inputs costs 1.7e-3 in the
                                 gradients, this format 2e-4). Same on all ranks. Default 0 */
-  SIGLIP_OPT_GRAD_TILE_N = 14 /* column-tile width of the gradient kernel: 0 (default) = choose by wave fill, 128, 256 */
+  SIGLIP_OPT_GRAD_TILE_N = 14, /* column-tile width of the gradient kernel: 0 (default) = choose by wave fill, 128, 256 */
+  SIGLIP_OPT_PEER_TIMEOUT_MS = 15, /* bound of every in-kernel wait on a PEER rank (text-ready / contribution-ready /
+                                      buffer-free flags, scalar exchange). Default 600000 (10 min, the order of a process
+                                      group's collective timeout: a peer may be late by a checkpoint save or an evaluation
+                                      pass); also settable by the environment variable SIGLIP_PEER_TIMEOUT_MS at context
+                                      creation. On expiry the kernel records the wait site and traps: the next call
+                                      returns SIGLIP_ERR_CUDA naming it. Waits on the kernel's own mbarriers keep their
+                                      4 s bound. */
+  SIGLIP_OPT_INKERNEL_SYNC = 16, /* 1 (default): siglip_fwd_bwd waits for / raises every cross-rank flag inside its tcgen05
+                                    kernels (a W-rank step is exactly 2W launches); 0: separate one-block wait / signal
+                                    kernels and a copy around them (A/B measurements) */
+  SIGLIP_OPT_SPLIT_K = 17, /* gradient kernel, tiles of a ragged last wave: -1 (default) choose, 0 never split, S = 2..8
+                              split each of them S ways along K (fp32 partials through a workspace, fixed-order sum:
+                              bitwise independent of which CTA finishes first) */
+  SIGLIP_OPT_AUX_TRACE = 18 /* 1: record globaltimer stamps of the auxiliary warps of CTA 0 for every launch (start,
+                               last peer flag seen, jobs done, end of launch); read with siglip_ctx_aux_trace */
 };
 
 /* Library / build identification: "siglip_b200 <version> sm_100a". */
@@ -85,6 +100,14 @@ int siglip_device_count(void);
  */
 int siglip_ctx_create(siglip_ctx** out, int device, int rank, int world, int B, int D);
 
+/*
+ * Same, for ranks with DIFFERENT batch sizes: batch_per_rank[p] is rank p's batch (every rank passes the same list).
+ * The reference cannot express this (its labels are gpu_batch_size x gpu_batch_size, distributed_sigmoid_loss.py:26-30,
+ * and all_gather needs equal shapes); semantics follow it where defined: rank r's loss sums its B_r images against all
+ * sum(B) texts and divides by ITS batch B_r (:47), the text gradient of rank c sums the contributions of every rank.
+ */
+int siglip_ctx_create_uneven(siglip_ctx** out, int device, int rank, int world, const int* batch_per_rank, int D);
+
 int siglip_ctx_set_option(siglip_ctx* ctx, int option, int value);
 
 /* Bytes of workspace the context holds on the device. */
@@ -102,16 +125,24 @@ int siglip_ctx_export_handles(siglip_ctx* ctx, void* out_bytes, size_t capacity)
 int siglip_ctx_import_handles(siglip_ctx* ctx, const void* all_ranks_bytes, size_t bytes_per_rank);
 
 /*
- * One training step of the loss (siglip_forward + siglip_backward with upstream gradient 1): replaces DDPSigmoidLoss.forward (distributed_sigmoid_loss.py:17-48) AND
+ * One training step of the loss, fused: replaces DDPSigmoidLoss.forward (distributed_sigmoid_loss.py:17-48) AND
  * the autograd backward of it, i.e. loss plus the four gradients for upstream grad 1:
  *   loss      [1]    = (1/B) sum_ij softplus(-y_ij z_ij)
  *   dimg      [B,D]  = dloss/dimg           (this rank's loss only)
  *   dtxt      [B,D]  = d(sum over ranks of their losses)/dtxt   (what all_gather's backward delivers)
  *   dt_prime  [1], dbias [1]                (this rank's loss only; DDP averages them later)
  * Collective: every rank of the context's world must call it the same number of times.
+ * Loss and gradient kernels alternate chunk by chunk (L0 L1 G1 L2 G2 ... G0), so only TWO [B, B] sigma operands exist
+ * however many ranks there are (the split siglip_forward / siglip_backward keep one per rank between the two calls),
+ * and every cross-rank flag is waited for / raised inside the kernels: a W-rank step is exactly 2W launches.
  */
 int siglip_fwd_bwd(siglip_ctx* ctx, const void* img, const void* txt, const float* t_prime, const float* bias,
                    float* loss, void* dimg, void* dtxt, float* dt_prime, float* dbias, void* cuda_stream);
+/* Same with an upstream gradient: every gradient is multiplied by *grad_out (device scalar; NULL = 1) in the kernel
+ * epilogues (autograd's grad_output of the loss, known before the step when the loss is the last node of the graph). */
+int siglip_fwd_bwd_scaled(siglip_ctx* ctx, const void* img, const void* txt, const float* t_prime, const float* bias,
+                          const float* grad_out, float* loss, void* dimg, void* dtxt, float* dt_prime, float* dbias,
+                          void* cuda_stream);
 
 /*
  * L2 normalisation fused around the loss (the step the reference's callers run immediately before it:
@@ -129,7 +160,7 @@ int siglip_normalize_bwd(siglip_ctx* ctx, const void* x, int in_bf16, const floa
                          int grad_bf16, void* dx, void* cuda_stream);
 
 /*
- * dst = src * (*g) elementwise over `nbytes` of fp32 (is_bf16 = 0) or bf16 (is_bf16 = 1) data: the whole
+ * dst = src * (*g) elementwise over `nbytes` (any whole number of elements) of fp32 (is_bf16 = 0) or bf16 (is_bf16 = 1) data: the whole
  * `backward()` of the module — the fused step already produced the gradients for an upstream gradient of 1
  * (replaces the autograd graph replay of SURVEY.md §3.2). `g` is a device scalar (grad_output).
  */
@@ -173,6 +204,11 @@ int siglip_fwd(siglip_ctx* ctx, const void* img, const void* txt, const float* t
  */
 int siglip_host_submit(siglip_ctx* ctx, const void* img_host, const void* txt_host, float t_prime, float bias,
                        unsigned long long* ticket, void* cuda_stream);
+/* Same, and the step's dimg / dtxt also travel back: bf16 [B, D] each into the given host buffers (both or neither),
+ * copied on a second internal copy stream so that the read-back of step n overlaps the kernels of step n+1. */
+int siglip_host_submit_grads(siglip_ctx* ctx, const void* img_host, const void* txt_host, float t_prime, float bias,
+                             void* dimg_host_bf16, void* dtxt_host_bf16, unsigned long long* ticket,
+                             void* cuda_stream);
 int siglip_host_wait(siglip_ctx* ctx, unsigned long long ticket, float* loss_host, float* dt_prime_host,
                      float* dbias_host);
 int siglip_fwd_bwd_host(siglip_ctx* ctx, const void* img_host, const void* txt_host, float t_prime, float bias,
@@ -206,13 +242,20 @@ int siglip_debug_gemm_timed(int device, int cta_group, int M, int N, int K, cons
 
 /*
  * Test hooks for exercising the multi-chunk schedule of ONE rank on ONE GPU (world > 1 context, no peers):
- * loopback wires every "peer" pointer to the context's own buffers; the test preloads the text chunks of the
- * other ranks, runs siglip_fwd_bwd, and reads this rank's per-owner dtxt contributions back. The dtxt output of
- * the step itself is meaningless in loopback mode (it sums the own slot world times).
+ * loopback wires every "peer" pointer to the context's own buffers (the peers' contribution slots to a zero buffer);
+ * the test preloads the text chunks of the other ranks, runs the step, and reads this rank's per-owner dtxt
+ * contributions back: slot c for c != rank, and the dtxt OUTPUT of the step for the own chunk (own contribution + the
+ * zero "peer" contributions).
  */
 int siglip_debug_loopback(siglip_ctx* ctx);
 int siglip_debug_set_text_chunk(siglip_ctx* ctx, int chunk, const void* txt_dev, void* cuda_stream);
 int siglip_debug_get_slot(siglip_ctx* ctx, int chunk, float* out_dev, void* cuda_stream);
+/* Loopback only: seed the (dt_prime, dbias) mailbox standing in for peer rank `peer`, so that the mean computed under
+ * SIGLIP_OPT_SYNC_SCALAR_GRADS can be checked against numbers the kernel did not produce itself. */
+int siglip_debug_set_mailbox(siglip_ctx* ctx, int peer, float dt_prime, float dbias);
+/* With SIGLIP_OPT_AUX_TRACE: device-synchronise and copy out 4 globaltimer stamps (ns) per launch since the last call
+ * (auxiliary warps of CTA 0: start, last peer flag observed (0 = no wait), jobs done; launch end as seen by the last CTA). */
+int siglip_ctx_aux_trace(siglip_ctx* ctx, unsigned long long* out, int max_launches, int* n_launches);
 
 void siglip_ctx_destroy(siglip_ctx* ctx);
 

@@ -43,6 +43,10 @@ CASES = [
     ("w2_b32_d512_f32", 2, 32, 512, float(np.log(10)), -10.0),  # BASELINE.json configs[0], raw fp32
     ("w1_b300_d136_f32", 1, 300, 136, float(np.log(10)), -10.0),
     ("w3_b40_d64_f32_warm", 3, 40, 64, float(np.log(25.0)), -4.5),
+    # BASELINE.json configs[4] embed dim (D = 1152 = 4.5 column tiles of 256): the "parity sweep vs
+    # rwightman_sigmoid_loss.py" — DDPSigmoidLoss and SigLipLoss (uni- and bidirectional ring) of the reference, W = 4, 8
+    ("w4_b40_d1152", 4, 40, 1152, float(np.log(10)), -10.0),
+    ("w8_b12_d1152_warm", 8, 12, 1152, float(np.log(25.0)), -4.5),
 ]
 
 

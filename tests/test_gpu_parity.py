@@ -54,6 +54,12 @@ def _scal(x):
     return torch.tensor([x], device=_dev(), dtype=torch.float32)
 
 
+def _contribution(eng, k, dtxt):
+    """This rank's contribution to the text gradient of chunk k in a loopback context: slot k for another rank's
+    chunk; for the own chunk the step's dtxt output (own contribution + the all-zero "peer" contributions)."""
+    return dtxt.float() if k == eng.rank else eng.debug_get_slot(k)
+
+
 # ---------------------------------------------------------------------------------------------------------
 # operand layouts of the tcgen05 mainloop
 # ---------------------------------------------------------------------------------------------------------
@@ -171,9 +177,13 @@ def test_multi_chunk_schedule_matches_reference_fixture(name):
         for k in range(W):
             eng.debug_set_text_chunk(k, _golden_rank_inputs(c, k)[1])
         img, txt = _golden_rank_inputs(c, r)
-        loss, dimg, _, dtp, db = eng.fwd_bwd(img, txt, _scal(c["t_prime"]), _scal(c["bias"]))
+        loss, dimg, dtxt, dtp, db = eng.fwd_bwd(img, txt, _scal(c["t_prime"]), _scal(c["bias"]))
+        n0 = eng.launch_count
+        loss2, dimg2, dtxt2, _, _ = eng.fwd_bwd(img, txt, _scal(c["t_prime"]), _scal(c["bias"]))   # step-to-step flags
+        assert eng.launch_count - n0 == 2 * W      # a W-chunk step is W loss + W gradient launches, nothing else
         loss_f = eng.fwd(img, txt, _scal(c["t_prime"]), _scal(c["bias"]))
         torch.cuda.synchronize()
+        assert torch.equal(loss, loss2) and torch.equal(dimg, dimg2) and torch.equal(dtxt, dtxt2)
         ref = c["variants"]["ddp"][r]
         _check(f"loss r{r}", loss, ref["loss"])
         _check(f"loss fwd r{r}", loss_f, ref["loss"])
@@ -181,12 +191,52 @@ def test_multi_chunk_schedule_matches_reference_fixture(name):
         _check(f"dt_prime r{r}", dtp, ref["dt_prime"])
         _check(f"dbias r{r}", db, ref["dbias"])
         for k in range(W):
-            dtxt_sum[k] += eng.debug_get_slot(k)
+            dtxt_sum[k] += _contribution(eng, k, dtxt)
         torch.cuda.synchronize()
         eng.close()
     for k in range(W):
         _check(f"dtxt owner {k}", dtxt_sum[k], c["variants"]["ddp"][k]["dtxt"])
         _check(f"dtxt owner {k} (ring variant)", dtxt_sum[k], c["variants"]["rw_uni"][k]["dtxt"])
+
+
+@pytest.mark.parametrize("name", ["w3_b5_d16", "w4_b8_d64", "w2_b24_d40_warm"])
+@pytest.mark.parametrize("inkernel", [1, 0])
+def test_split_api_and_helper_launch_variant_match_reference_fixture(name, inkernel):
+    """The same loopback replay through (a) the split siglip_forward / siglip_backward API (one sigma operand per chunk
+    kept between the calls, grad_out folded into the epilogues) and (b) the fused step with SIGLIP_OPT_INKERNEL_SYNC
+    = 0 (flags handled by separate one-block kernels): identical results to the fused in-kernel default."""
+    from distributed_sigmoid_loss_b200 import _capi
+    c = load_golden(name)
+    W, B, D = c["world"], c["batch"], c["dim"]
+    dtxt_split = [torch.zeros(B, D, device=_dev()) for _ in range(W)]
+    for r in range(W):
+        eng = _engine(B, D, 2, rank_world=(r, W), loopback=True)
+        eng.set_option(_capi.SIGLIP_OPT_INKERNEL_SYNC, inkernel)
+        for k in range(W):
+            eng.debug_set_text_chunk(k, _golden_rank_inputs(c, k)[1])
+        img, txt = _golden_rank_inputs(c, r)
+        tp, b = _scal(c["t_prime"]), _scal(c["bias"])
+        loss_a, dimg_a, dtxt_a, dtp_a, db_a = eng.fwd_bwd(img, txt, tp, b)
+        slots_a = [_contribution(eng, k, dtxt_a).clone() for k in range(W)]
+        loss_b = eng.forward(img, txt, tp, b, True)
+        dimg_b, dtxt_b, dtp_b, db_b = eng.backward(img, txt, tp, None)
+        torch.cuda.synchronize()
+        ref = c["variants"]["ddp"][r]
+        _check(f"loss r{r}", loss_b, ref["loss"])
+        _check(f"dimg r{r}", dimg_b, ref["dimg"])
+        _check(f"dt_prime r{r}", dtp_b, ref["dt_prime"])
+        _check(f"dbias r{r}", db_b, ref["dbias"])
+        # same kernels on the same operands: the two schedules agree to the last bit
+        assert torch.equal(loss_a, loss_b) and torch.equal(dimg_a, dimg_b)
+        assert torch.equal(dtp_a, dtp_b) and torch.equal(db_a, db_b)
+        for k in range(W):
+            got = dtxt_b.float() if k == r else eng.debug_get_slot(k)
+            assert torch.equal(got, slots_a[k])
+            dtxt_split[k] += got
+        torch.cuda.synchronize()
+        eng.close()
+    for k in range(W):
+        _check(f"dtxt owner {k}", dtxt_split[k], c["variants"]["ddp"][k]["dtxt"])
 
 
 # ---------------------------------------------------------------------------------------------------------
@@ -253,14 +303,14 @@ def test_two_chunks_large_loopback():
         eng = _engine(B, D, 2, rank_world=(r, W), loopback=True)
         for k in range(W):
             eng.debug_set_text_chunk(k, chunks[k])
-        loss, dimg, _, dtp, db = eng.fwd_bwd(img, chunks[r], _scal(math.log(10.0)), _scal(-10.0))
+        loss, dimg, dtxt, dtp, db = eng.fwd_bwd(img, chunks[r], _scal(math.log(10.0)), _scal(-10.0))
         torch.cuda.synchronize()
         _check("loss", loss, ref["loss"])
         _check("dimg", dimg, ref["dimg"])
         _check("dt_prime", dtp, ref["dt_prime"])
         _check("dbias", db, ref["dbias"])
         for k in range(W):
-            _check(f"dtxt contribution to owner {k}", eng.debug_get_slot(k), ref["dtxt_chunks"][k])
+            _check(f"dtxt contribution to owner {k}", _contribution(eng, k, dtxt), ref["dtxt_chunks"][k])
         eng.close()
 
 
@@ -519,30 +569,67 @@ def test_kernel_launch_accounting():
     lm, ln, gm, gn = eng.kernel_times()
     assert ln == 1 and gn == 1 and lm > 0 and gm > 0
     eng.close()
+    # a 3-chunk step (loopback): 3 loss + 3 gradient launches; with the helper-launch variant 11 more
+    # (wait, copy is a memcpy, signal | signal | wait | 2 signals | signal: wait x2 + signal x5 kernels)
+    e3 = _engine(B, D, 2, rank_world=(0, 3), loopback=True)
+    for k in range(3):
+        e3.debug_set_text_chunk(k, txt)
+    e3.fwd_bwd(img, txt, _scal(1.0), _scal(-5.0))
+    n0 = e3.launch_count
+    e3.fwd_bwd(img, txt, _scal(1.0), _scal(-5.0))
+    assert e3.launch_count - n0 == 6
+    e3.set_option(_capi.SIGLIP_OPT_INKERNEL_SYNC, 0)
+    n0 = e3.launch_count
+    e3.fwd_bwd(img, txt, _scal(1.0), _scal(-5.0))
+    assert e3.launch_count - n0 == 6 + 7
+    torch.cuda.synchronize()
+    e3.close()
 
 
 def test_scalar_gradient_mean_option_loopback():
-    """SIGLIP_OPT_SYNC_SCALAR_GRADS on a loopback context (every 'peer' mailbox is my own): the one-warp exchange runs
-    its full signal / wait / gather protocol and the mean of W copies equals the local value, step after step.
-    (Real peers: tools/multi_gpu_check.py.)"""
+    """SIGLIP_OPT_SYNC_SCALAR_GRADS on a loopback context: the one-warp exchange runs its full signal / wait / gather
+    protocol; the "peers'" mailboxes are seeded with DISTINCT values the kernel did not produce (debug hook), so the
+    mean it returns is checked against (own + seeded values) / W in rank order — a skipped peer, a wrong peer or a wrong
+    divisor fails (test_distributed_sigmoid_loss.py:79-83 semantics: all_reduce SUM, then / size)."""
     from distributed_sigmoid_loss_b200 import _capi
-    B, D, W = 256, 128, 3
+    B, D, W = 256, 128, 4
+    me = 1
     img, txt = _synth(B, D, seed=5)
     tp, b = _scal(math.log(10.0)), _scal(-10.0)
-    eng = _engine(B, D, 2, rank_world=(1, W), loopback=True)
+    eng = _engine(B, D, 2, rank_world=(me, W), loopback=True)
     for k in range(W):
         eng.debug_set_text_chunk(k, _synth(B, D, seed=20 + k)[1])
     _, _, _, dtp0, db0 = eng.fwd_bwd(img, txt, tp, b)
+    torch.cuda.synchronize()
+    seeded = {0: (0.37, -1.25), 2: (-4.5, 0.03125), 3: (11.0, 2.75)}
+    for p, (a_, b_) in seeded.items():
+        eng.debug_set_mailbox(p, a_, b_)
     eng.set_option(_capi.SIGLIP_OPT_SYNC_SCALAR_GRADS, 1)
-    for _ in range(3):
-        _, _, _, dtp1, db1 = eng.fwd_bwd(img, txt, tp, b)
-        torch.cuda.synchronize()
-        assert abs(float(dtp1) - float(dtp0)) <= 1e-6 * abs(float(dtp0))
-        assert abs(float(db1) - float(db0)) <= 1e-6 * abs(float(db0))
+
+    def expect(own, idx):
+        acc = np.float32(0.0)
+        for p in range(W):       # the kernel adds the W mailboxes in rank order in fp32
+            acc = np.float32(acc + (np.float32(own) if p == me else np.float32(seeded[p][idx])))
+        return float(np.float32(acc * np.float32(1.0 / W)))
+    for rep in range(3):
+        for fused in (True, False):
+            if fused:
+                _, _, _, dtp1, db1 = eng.fwd_bwd(img, txt, tp, b)
+            else:
+                eng.forward(img, txt, tp, b, True)
+                _, _, dtp1, db1 = eng.backward(img, txt, tp, None)
+            torch.cuda.synchronize()
+            assert float(dtp1) == expect(float(dtp0), 0), (float(dtp1), expect(float(dtp0), 0))
+            assert float(db1) == expect(float(db0), 1), (float(db1), expect(float(db0), 1))
+    # a different seed for ONE peer must move the result (that peer is really read)
+    eng.debug_set_mailbox(3, 12.0, 2.75)
+    _, _, _, dtp2, _ = eng.fwd_bwd(img, txt, tp, b)
+    torch.cuda.synchronize()
+    assert abs(float(dtp2) - float(dtp1) - 0.25) < 1e-5
     eng.close()
 
 
-@pytest.mark.parametrize("name", ["w4_b8_d64", "w5_b4_d32"])
+@pytest.mark.parametrize("name", ["w4_b8_d64", "w5_b4_d32", "w4_b40_d1152", "w8_b12_d1152_warm"])
 def test_bidirectional_order_matches_reference_fixture(name):
     """SIGLIP_OPT_BIDIR (chunks visited right, left, right+1, ... like rwightman_sigmoid_loss.py:75-107): same pairs,
     so the loopback replay of every rank must reproduce the reference's bidirectional-variant outputs."""
@@ -559,7 +646,7 @@ def test_bidirectional_order_matches_reference_fixture(name):
         for k in range(W):
             eng.debug_set_text_chunk(k, _golden_rank_inputs(c, k)[1])
         img, txt = _golden_rank_inputs(c, r)
-        loss, dimg, _, dtp, db = eng.fwd_bwd(img, txt, _scal(c["t_prime"]), _scal(c["bias"]))
+        loss, dimg, dtxt, dtp, db = eng.fwd_bwd(img, txt, _scal(c["t_prime"]), _scal(c["bias"]))
         torch.cuda.synchronize()
         ref = c["variants"][variant][r]
         _check(f"loss r{r}", loss, ref["loss"])
@@ -567,7 +654,7 @@ def test_bidirectional_order_matches_reference_fixture(name):
         _check(f"dt_prime r{r}", dtp, ref["dt_prime"])
         _check(f"dbias r{r}", db, ref["dbias"])
         for k in range(W):
-            dtxt_sum[k] += eng.debug_get_slot(k)
+            dtxt_sum[k] += _contribution(eng, k, dtxt)
         torch.cuda.synchronize()
         eng.close()
     for k in range(W):
@@ -661,7 +748,7 @@ def test_fp32_inputs_multi_chunk_schedule_matches_raw_fp32_fixture(name):
             eng.debug_set_text_chunk(k, eng.convert_f32(_raw_rank_inputs(c, k)[1], True))
         img, txt = _raw_rank_inputs(c, r)
         ih, th = eng.convert_f32(img, True), eng.convert_f32(txt, True)
-        loss, dimg, _, dtp, db = eng.fwd_bwd(ih, th, _scal(c["t_prime"]), _scal(c["bias"]))
+        loss, dimg, dtxt, dtp, db = eng.fwd_bwd(ih, th, _scal(c["t_prime"]), _scal(c["bias"]))
         torch.cuda.synchronize()
         ref = c["variants"]["ddp"][r]
         _check(f"loss r{r}", loss, ref["loss"])
@@ -669,7 +756,7 @@ def test_fp32_inputs_multi_chunk_schedule_matches_raw_fp32_fixture(name):
         _check(f"dt_prime r{r}", dtp, ref["dt_prime"])
         _check(f"dbias r{r}", db, ref["dbias"])
         for k in range(W):
-            dtxt_sum[k] += eng.debug_get_slot(k)
+            dtxt_sum[k] += _contribution(eng, k, dtxt)
         torch.cuda.synchronize()
         eng.close()
     for k in range(W):
@@ -694,4 +781,305 @@ def test_gradient_column_tile_width_does_not_change_the_result(shape, cg):
         out[tn] = (dimg.clone(), dtxt.clone())
     assert torch.equal(out[128][0], out[256][0]) and torch.equal(out[128][1], out[256][1])
     assert torch.equal(out[0][0], out[256][0]) and torch.equal(out[0][1], out[256][1])
+    eng.close()
+
+
+# ---------------------------------------------------------------------------------------------------------
+# the remaining BASELINE.json configs: configs[2] (B=8192/rank, D=768) and configs[4] (B=32768/rank, D=1152)
+# ---------------------------------------------------------------------------------------------------------
+def test_config2_shape_single_chunk_and_two_chunk_loopback():
+    """BASELINE.json configs[2] per-rank shape (B=8192, D=768): one chunk against fp32 autograd, then rank 1 of a
+    2-rank job (loopback): loss / dimg / scalars and both dtxt contributions against fp32 autograd of the 2-chunk loss."""
+    from oracle.siglip_oracle import torch_reference_fp32
+
+    B, D = 8192, 768
+    tp, bias = math.log(10.0), -10.0
+    img, txt = _synth(B, D)
+    ref = torch_reference_fp32(img, [txt], tp, bias, 0)
+    eng = _engine(B, D, 2)
+    loss, dimg, dtxt, dtp, db = eng.fwd_bwd(img, txt, _scal(tp), _scal(bias))
+    torch.cuda.synchronize()
+    _check("loss", loss, ref["loss"])
+    _check("dimg", dimg, ref["dimg"])
+    _check("dtxt", dtxt, ref["dtxt_chunks"][0])
+    _check("dt_prime", dtp, ref["dt_prime"])
+    _check("dbias", db, ref["dbias"])
+    eng.close()
+    del ref
+    _, txt0 = _synth(B, D, 77)
+    chunks = [txt0, txt]                       # rank 1 owns chunk 1
+    ref = torch_reference_fp32(img, chunks, tp, bias, 1)
+    eng = _engine(B, D, 2, rank_world=(1, 2), loopback=True)
+    eng.debug_set_text_chunk(0, txt0)
+    eng.debug_set_text_chunk(1, txt)
+    loss, dimg, dtxt, dtp, db = eng.fwd_bwd(img, txt, _scal(tp), _scal(bias))
+    torch.cuda.synchronize()
+    assert eng.workspace_bytes < 3 * 2 * B * B + (1 << 30)     # two sigma operands + O(B D) buffers
+    _check("loss (2 chunks)", loss, ref["loss"])
+    _check("dimg (2 chunks)", dimg, ref["dimg"])
+    _check("dt_prime (2 chunks)", dtp, ref["dt_prime"])
+    _check("dbias (2 chunks)", db, ref["dbias"])
+    for k in range(2):
+        _check(f"dtxt contribution to owner {k}", _contribution(eng, k, dtxt), ref["dtxt_chunks"][k])
+    eng.close()
+
+
+def test_config4_shape_single_chunk():
+    """BASELINE.json configs[4] per-rank shape (B=32768, D=1152): one full chunk against fp32 autograd on the GPU
+    (a 32768 x 32768 fp32 logits matrix is 4 GiB; autograd keeps a handful of them: fits the 180 GB), plus the
+    size-independent identities."""
+    from oracle.siglip_oracle import torch_reference_fp32
+
+    B, D = 32768, 1152
+    tp, bias = math.log(10.0), -10.0
+    img, txt = _synth(B, D)
+    eng = _engine(B, D, 2)
+    loss, dimg, dtxt, dtp, db = eng.fwd_bwd(img, txt, _scal(tp), _scal(bias))
+    loss2, dimg2, dtxt2, dtp2, db2 = eng.fwd_bwd(img, txt, _scal(tp), _scal(bias))
+    torch.cuda.synchronize()
+    assert torch.equal(loss, loss2) and torch.equal(dimg, dimg2) and torch.equal(dtxt, dtxt2)
+    s_img = float((dimg.double() * img.double()).sum())
+    s_txt = float((dtxt.double() * txt.double()).sum())
+    assert abs(s_img - float(dtp)) <= 1e-3 * abs(float(dtp)) and abs(s_txt - float(dtp)) <= 1e-3 * abs(float(dtp))
+    eng.close()
+    ref = torch_reference_fp32(img, [txt], tp, bias, 0)
+    _check("loss", loss, ref["loss"])
+    _check("dimg", dimg, ref["dimg"])
+    _check("dtxt", dtxt, ref["dtxt_chunks"][0])
+    _check("dt_prime", dtp, ref["dt_prime"])
+    _check("dbias", db, ref["dbias"])
+
+
+@pytest.mark.parametrize("name", ["w4_b40_d1152", "w8_b12_d1152_warm"])
+def test_d1152_sweep_against_both_reference_variants(name):
+    """configs[4] "parity sweep vs rwightman_sigmoid_loss.py": D = 1152 fixtures produced by the unmodified reference's
+    DDPSigmoidLoss AND SigLipLoss (uni- and bidirectional ring, rwightman_sigmoid_loss.py:68-124); every rank of the
+    W = 4 / 8 job replayed on one GPU in the unidirectional order (the bidirectional order is the test above)."""
+    c = load_golden(name)
+    W, B, D = c["world"], c["batch"], c["dim"]
+    dtxt_sum = [torch.zeros(B, D, device=_dev()) for _ in range(W)]
+    for r in range(W):
+        eng = _engine(B, D, 2, rank_world=(r, W), loopback=True)
+        for k in range(W):
+            eng.debug_set_text_chunk(k, _golden_rank_inputs(c, k)[1])
+        img, txt = _golden_rank_inputs(c, r)
+        loss, dimg, dtxt, dtp, db = eng.fwd_bwd(img, txt, _scal(c["t_prime"]), _scal(c["bias"]))
+        torch.cuda.synchronize()
+        for variant in ("ddp", "rw_uni", "rw_bidir"):
+            ref = c["variants"][variant][r]
+            _check(f"{variant} loss r{r}", loss, ref["loss"])
+            _check(f"{variant} dimg r{r}", dimg, ref["dimg"])
+            _check(f"{variant} dt_prime r{r}", dtp, ref["dt_prime"])
+            _check(f"{variant} dbias r{r}", db, ref["dbias"])
+        for k in range(W):
+            dtxt_sum[k] += _contribution(eng, k, dtxt)
+        torch.cuda.synchronize()
+        eng.close()
+    for k in range(W):
+        for variant in ("ddp", "rw_uni", "rw_bidir"):
+            _check(f"{variant} dtxt owner {k}", dtxt_sum[k], c["variants"][variant][k]["dtxt"])
+
+
+# ---------------------------------------------------------------------------------------------------------
+# SURVEY.md §8(f)4: uneven per-rank batch
+# ---------------------------------------------------------------------------------------------------------
+def _uneven_closed_form(img_blocks, txt_blocks, tp, bias):
+    """float64 closed form for ranks with different batches (distributed_sigmoid_loss.py:22-47 semantics where they
+    are defined: rank r sums its B_r images against all texts and divides by ITS batch; labels +1 on the own chunk's
+    diagonal). Returns per rank: loss, dimg, dt', db, and contrib[r][c] = rank r's contribution to chunk c's dtxt."""
+    t = math.exp(tp)
+    out = []
+    for r, img in enumerate(img_blocks):
+        img = img.astype(np.float64)
+        br = img.shape[0]
+        res = dict(loss=0.0, dimg=np.zeros_like(img), dtp=0.0, db=0.0, contrib=[])
+        for c, txt in enumerate(txt_blocks):
+            txt = txt.astype(np.float64)
+            s = img @ txt.T
+            z = t * s + bias
+            y = -np.ones_like(z)
+            if c == r:
+                y[np.arange(br), np.arange(br)] = 1.0
+            e = np.exp(-np.abs(-y * z))
+            sig = np.where(-y * z >= 0, 1.0 / (1.0 + e), e / (1.0 + e))        # sigma(-y z)
+            g = -y * sig / br
+            res["loss"] += float((np.maximum(-y * z, 0.0) + np.log1p(e)).sum() / br)
+            res["dimg"] += t * (g @ txt)
+            res["contrib"].append(t * (g.T @ img))
+            res["dtp"] += float(t * (g * s).sum())
+            res["db"] += float(g.sum())
+        out.append(res)
+    return out
+
+
+def test_uneven_per_rank_batches_loopback():
+    """Ranks with B = (40, 24, 33) (siglip_ctx_create_uneven): every rank replayed on one GPU; per-rank loss / dimg /
+    scalars and the per-owner dtxt sums against the float64 closed form."""
+    Bs, D = (40, 24, 33), 72
+    W = len(Bs)
+    tp, bias = math.log(10.0), -8.0
+    g = torch.Generator().manual_seed(31)
+    imgs = [torch.nn.functional.normalize(torch.randn(b, D, generator=g)).to(torch.bfloat16) for b in Bs]
+    txts = [torch.nn.functional.normalize(torch.randn(b, D, generator=g)).to(torch.bfloat16) for b in Bs]
+    ref = _uneven_closed_form([x.float().numpy() for x in imgs], [x.float().numpy() for x in txts], tp, bias)
+    for sched in ("fused", "split"):
+        dtxt_sum = [torch.zeros(b, D, device=_dev()) for b in Bs]
+        for r in range(W):
+            eng = _engine(Bs[r], D, 2, rank_world=(r, W), loopback=True, batch_per_rank=Bs)
+            for k in range(W):
+                eng.debug_set_text_chunk(k, txts[k].to(_dev()))
+            img, txt = imgs[r].to(_dev()), txts[r].to(_dev())
+            if sched == "fused":
+                loss, dimg, dtxt, dtp, db = eng.fwd_bwd(img, txt, _scal(tp), _scal(bias))
+            else:
+                loss = eng.forward(img, txt, _scal(tp), _scal(bias), True)
+                dimg, dtxt, dtp, db = eng.backward(img, txt, _scal(tp), None)
+            torch.cuda.synchronize()
+            _check(f"{sched} loss r{r}", loss, ref[r]["loss"])
+            _check(f"{sched} dimg r{r}", dimg, ref[r]["dimg"])
+            _check(f"{sched} dt_prime r{r}", dtp, ref[r]["dtp"])
+            _check(f"{sched} dbias r{r}", db, ref[r]["db"])
+            for k in range(W):
+                got = _contribution(eng, k, dtxt)
+                assert tuple(got.shape) == (Bs[k], D)
+                _check(f"{sched} contribution r{r} -> owner {k}", got, ref[r]["contrib"][k])
+                dtxt_sum[k] += got
+            eng.close()
+        for k in range(W):
+            _check(f"{sched} dtxt owner {k}", dtxt_sum[k], sum(ref[r]["contrib"][k] for r in range(W)))
+    with pytest.raises(RuntimeError):
+        _engine(40, D, 2, rank_world=(1, W), loopback=True, batch_per_rank=Bs)    # rank 1's batch is 24, not 40
+
+
+# ---------------------------------------------------------------------------------------------------------
+# module surface: fused schedule, odd embedding widths, views, siglip_scale on any size
+# ---------------------------------------------------------------------------------------------------------
+def test_module_fused_schedule_equals_split_schedule():
+    """DDPSigmoidLoss(fused_step=True) (what a multi-rank group uses by default) against fused_step=False: the fused
+    step leaves gradients for an upstream gradient of 1 and backward() multiplies by grad_output — same numbers up to
+    the order of the two roundings (fp32 result x g, then bf16)."""
+    from distributed_sigmoid_loss_b200 import DDPSigmoidLoss
+    B, D = 640, 192
+    img, txt = _synth(B, D, seed=9)
+    outs = []
+    for fused in (False, True):
+        mod = DDPSigmoidLoss(B, fused_step=fused).to(_dev())
+        a, b = img.clone().requires_grad_(True), txt.clone().requires_grad_(True)
+        loss = mod(a, b)
+        (0.5 * loss).backward()
+        torch.cuda.synchronize()
+        outs.append((loss.detach(), a.grad, b.grad, mod.t_prime.grad, mod.bias.grad))
+    assert torch.equal(outs[0][0], outs[1][0])
+    _check("dimg", outs[1][1].float(), outs[0][1].float(), tol=4e-3)
+    _check("dtxt", outs[1][2].float(), outs[0][2].float(), tol=4e-3)
+    _check("dt_prime", outs[1][3], float(outs[0][3]), tol=1e-6)
+    _check("dbias", outs[1][4], float(outs[0][4]), tol=1e-6)
+    # fp32 leaves take the fp32-gradient route in both schedules: equal to 1e-6
+    g32 = []
+    for fused in (False, True):
+        mod = DDPSigmoidLoss(B, fused_step=fused).to(_dev())
+        a = img.float().requires_grad_(True)
+        mod(a, txt.float()).backward()
+        torch.cuda.synchronize()
+        g32.append(a.grad)
+    _check("fp32 dimg", g32[1], g32[0], tol=1e-6)
+
+
+def test_module_accepts_any_embedding_width_and_views():
+    """The reference's own test uses output_dim = 2 (test_distributed_sigmoid_loss.py:144): widths that are not a
+    multiple of 8 are zero-padded (zero columns change no dot product) and the gradient comes back sliced;
+    non-contiguous and 16-byte-misaligned views are copied instead of rejected."""
+    from distributed_sigmoid_loss_b200 import DDPSigmoidLoss
+    from oracle.siglip_oracle import torch_reference_fp32
+    B = 96
+    for D in (2, 20, 515):
+        g = torch.Generator().manual_seed(D)
+        img = torch.nn.functional.normalize(torch.randn(B, D, generator=g)).to(_dev())
+        txt = torch.nn.functional.normalize(torch.randn(B, D, generator=g)).to(_dev())
+        ref = torch_reference_fp32(img, [txt], math.log(10.0), -10.0, 0)
+        mod = DDPSigmoidLoss(B).to(_dev())
+        a, b = img.clone().requires_grad_(True), txt.clone().requires_grad_(True)
+        loss = mod(a, b)
+        loss.backward()
+        torch.cuda.synchronize()
+        assert a.grad.shape == (B, D) and b.grad.shape == (B, D)
+        _check(f"D={D} loss", loss.detach(), ref["loss"])
+        _check(f"D={D} dimg", a.grad, ref["dimg"])
+        _check(f"D={D} dtxt", b.grad, ref["dtxt_chunks"][0])
+    # a misaligned, strided view of a larger bf16 buffer
+    D = 64
+    big = torch.nn.functional.normalize(torch.randn(B, 2 * D + 3, device=_dev())).to(torch.bfloat16)
+    view = big[:, 3:3 + D]
+    assert view.data_ptr() % 16 != 0 and not view.is_contiguous()
+    txt = _synth(B, D, 3)[1]
+    mod = DDPSigmoidLoss(B).to(_dev())
+    l_view = mod(view, txt)
+    l_copy = mod(view.clone(), txt)
+    torch.cuda.synchronize()
+    assert torch.equal(l_view, l_copy)
+
+
+def test_scale_any_size_and_alignment():
+    eng = _engine(256, 64, 2)
+    g = _scal(-0.75)
+    for n in (1, 7, 8, 1000, 4099):
+        for dt in (torch.float32, torch.bfloat16):
+            x = torch.randn(n + 3, device=_dev()).to(dt)
+            for off in (0, 1, 3):
+                v = x[off:off + n]
+                want = (v.float() * -0.75).to(dt)
+                assert torch.equal(eng.scale(v, g), want), (n, dt, off)
+    with pytest.raises(RuntimeError):
+        eng.scale(torch.zeros(4, device=_dev(), dtype=torch.float16), g)
+    eng.close()
+
+
+def test_host_entry_returns_bf16_gradients():
+    """siglip_host_submit_grads: the bf16 gradients of every pipelined step arrive in the caller's host buffers and equal
+    the device entry's bf16 gradients bit for bit."""
+    B, D = 1024, 256
+    eng = _engine(B, D, 2)
+    want, tickets = [], []
+    hosts = []
+    for i in range(4):
+        img, txt = _synth(B, D, seed=500 + i)
+        tp, bias = math.log(10.0) + 0.1 * i, -10.0 + i
+        loss, dimg, dtxt, _, _ = eng.fwd_bwd(img, txt, _scal(tp), _scal(bias), torch.bfloat16)
+        torch.cuda.synchronize()
+        want.append((float(loss), dimg.cpu(), dtxt.cpu()))
+        hosts.append((img.cpu().pin_memory(), txt.cpu().pin_memory(), tp, bias,
+                      torch.empty(B, D, dtype=torch.bfloat16).pin_memory(),
+                      torch.empty(B, D, dtype=torch.bfloat16).pin_memory()))
+    prev = None
+    got = []
+    for (ih, th, tp, bias, gi, gt) in hosts:
+        t = eng.host_submit(ih, th, tp, bias, gi, gt)
+        if prev is not None:
+            got.append(eng.host_wait(prev))
+        prev = t
+    got.append(eng.host_wait(prev))
+    for i in range(4):
+        assert got[i][0] == want[i][0]
+        assert torch.equal(hosts[i][4], want[i][1]) and torch.equal(hosts[i][5], want[i][2])
+    with pytest.raises(RuntimeError):
+        eng.host_submit(hosts[0][0], hosts[0][1], 1.0, 1.0, hosts[0][4], None)
+    eng.close()
+
+
+def test_peer_timeout_option_and_trace_hook():
+    from distributed_sigmoid_loss_b200 import _capi
+    B, D = 256, 64
+    img, txt = _synth(B, D)
+    eng = _engine(B, D, 2, rank_world=(0, 2), loopback=True)
+    eng.set_option(_capi.SIGLIP_OPT_PEER_TIMEOUT_MS, 5000)
+    with pytest.raises(RuntimeError):
+        eng.set_option(_capi.SIGLIP_OPT_PEER_TIMEOUT_MS, 0)
+    eng.debug_set_text_chunk(0, txt)
+    eng.debug_set_text_chunk(1, txt)
+    eng.set_option(_capi.SIGLIP_OPT_AUX_TRACE, 1)
+    eng.fwd_bwd(img, txt, _scal(1.0), _scal(-5.0))
+    tr = eng.aux_trace()
+    assert len(tr) == 4                       # L0 L1 G1 G0
+    for (t0, tflag, tdone, tend) in tr:
+        assert t0 > 0 and tdone >= t0 and (tend == 0 or tend >= t0)
     eng.close()
