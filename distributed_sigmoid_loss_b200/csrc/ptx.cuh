@@ -271,6 +271,27 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint6
   }
 }
 
+// Same with 8-bit operands (kind::f8f6f4; here e4m3 x e4m3 -> fp32): K = 32 per instruction. Measurement path only.
+template <int kCG>
+__device__ __forceinline__ void umma_f8(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                        uint32_t accumulate) {
+  if constexpr (kCG == 1) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f8f6f4 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+  } else {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f8f6f4 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+  }
+}
+
 // All previously issued MMAs of this thread -> arrive(1) on `bar` when they retire.
 // kCG == 2: arrive on the same barrier offset in both CTAs of the pair.
 template <int kCG>
@@ -341,6 +362,7 @@ __device__ __forceinline__ uint64_t make_smem_desc_sw128(uint32_t saddr, uint32_
 //   [4,6) D fmt (1 = f32)  [7,10) A fmt (1 = bf16)  [10,13) B fmt (1 = bf16)
 //   [15] A major (1 = MN)  [16] B major (1 = MN)    [17,23) N >> 3          [24,29) M >> 4
 //   ab_f16: both operands hold IEEE fp16 instead of bf16 (mixing fp16 with bf16 in one MMA faults on sm_100a)
+//   ab_f16 == 2: kind::f8f6f4 with e4m3 operands (format code 0 in both fields)
 __host__ __device__ constexpr uint32_t make_idesc_bf16(int m, int n, int a_mn_major, int b_mn_major,
                                                        int ab_f16 = 0) {
   return (1u << 4) | ((ab_f16 ? 0u : 1u) << 7) | ((ab_f16 ? 0u : 1u) << 10) |

@@ -90,6 +90,23 @@ int encode_bf16_2d(CUtensorMap* m, const void* base, uint64_t inner, uint64_t ou
   return 0;
 }
 
+// 8-bit K-major operand [rows][K bytes]: 128-byte (= 128 element) swizzle rows
+int encode_u8_kmajor(CUtensorMap* m, const void* base, int rows, int K, long long ld, int box_rows) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (fn == nullptr) return fail(SIGLIP_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+  if ((reinterpret_cast<uintptr_t>(base) & 15u) != 0 || (ld % 16) != 0)
+    return fail(SIGLIP_ERR_INVALID, "8-bit operand needs a 16-byte aligned base and row stride");
+  cuuint64_t dims[2] = {static_cast<cuuint64_t>(K), static_cast<cuuint64_t>(rows)};
+  cuuint64_t strides[1] = {static_cast<cuuint64_t>(ld)};
+  cuuint32_t box[2] = {128, static_cast<cuuint32_t>(box_rows)};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(SIGLIP_ERR_CUDA, "cuTensorMapEncodeTiled (uint8) failed");
+  return 0;
+}
+
 // Operand tensor map for the mainloop. mn == 0: stored [rows][K]; mn == 1: stored [K][rows].
 int encode_operand(CUtensorMap* m, const void* base, int rows, int K, long long ld, int mn, int box_rows_kmajor) {
   if (!mn) return encode_bf16_2d(m, base, (uint64_t)K, (uint64_t)rows, (uint64_t)ld, 64, (uint32_t)box_rows_kmajor);
@@ -181,7 +198,6 @@ struct siglip_ctx {
   unsigned long long* aux_trace = nullptr;  // [kTraceLaunches][4] globaltimer stamps (SIGLIP_OPT_AUX_TRACE)
   float* splitk_ws = nullptr;            // fp32 partial accumulators of the split tiles of the gradient kernel
   unsigned int* splitk_counters = nullptr;  // per split tile: arrivals of the non-owner parts (monotonic)
-  unsigned int splitk_epoch = 0;
   size_t splitk_ws_bytes = 0;
   unsigned int aux_trace_n = 0;
   // peers (index = rank); own entries point at local memory
@@ -272,6 +288,20 @@ int ensure_g(siglip_ctx* c, int i) {
     return fail(SIGLIP_ERR_CUDA, buf);
   }
   c->workspace_bytes += gbytes + tbytes;
+  return 0;
+}
+
+// Workspace of the gradient kernel's split-K (fp32 partial accumulators of the tiles of a ragged last wave): fewer than
+// one 256 KiB partial per SM pair can ever be outstanding.
+constexpr int kSplitKMaxTiles = 160;
+int ensure_splitk(siglip_ctx* c) {
+  if (c->splitk_ws != nullptr) return 0;
+  const size_t bytes = static_cast<size_t>(c->num_sms + 2) * 128 * 256 * sizeof(float);
+  CK(cudaMalloc(reinterpret_cast<void**>(&c->splitk_ws), bytes));
+  CK(cudaMalloc(reinterpret_cast<void**>(&c->splitk_counters), 2 * kSplitKMaxTiles * sizeof(unsigned int)));
+  CK(cudaMemset(c->splitk_counters, 0, 2 * kSplitKMaxTiles * sizeof(unsigned int)));
+  c->splitk_ws_bytes = bytes;
+  c->workspace_bytes += bytes;
   return 0;
 }
 
@@ -513,6 +543,14 @@ int run_grad_chunk(siglip_ctx* c, int gi, bool own, const void* img, const __nv_
   p.grad_out = grad_out;
   p.inv_b = 1.0f / static_cast<float>(c->B);
   p.dbg = c->dbg_dev;
+  if (c->split_k != 0 && c->mcast == 1) {
+    if ((rc = ensure_splitk(c))) return rc;
+    p.sk_request = c->split_k;
+    p.sk_ws = c->splitk_ws;
+    p.sk_ws_bytes = c->splitk_ws_bytes;
+    p.sk_counters = c->splitk_counters;
+    p.sk_max_tiles = kSplitKMaxTiles;
+  }
   apply_aux(c, p, aux, end);
   if ((rc = timing_mark(c, c->ev_grad, c->ev_grad_used, st))) return rc;
   CKI(siglip::launch_gemm(cg, siglip::kModeOut, c->stages_grad, c->mcast, &tmA0, &tmB0, &tmA1, &tmB1,
@@ -1525,10 +1563,17 @@ int siglip_debug_gemm_timed(int device, int cta_group, int M, int N, int K, cons
   CK(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, device));
   CUtensorMap tmA, tmB;
   int rc;
-  if ((rc = encode_operand(&tmA, A, M, K, lda, a_mn, 128))) return rc;
+  const bool fp8 = getenv("SIGLIP_DEBUG_AB_FP8") != nullptr;   // A, B hold e4m3 bytes, K-major (kind::f8f6f4)
   const char* env_mc = getenv("SIGLIP_DEBUG_MCAST");
   const int mcast = env_mc ? atoi(env_mc) : 1;
-  if ((rc = encode_operand(&tmB, Bm, N, K, ldb, b_mn, 256 / (cta_group * mcast)))) return rc;
+  if (fp8) {
+    if (a_mn || b_mn || mcast != 1) return fail(SIGLIP_ERR_INVALID, "the fp8 measurement path is K-major, no multicast");
+    if ((rc = encode_u8_kmajor(&tmA, A, M, K, lda, 128))) return rc;
+    if ((rc = encode_u8_kmajor(&tmB, Bm, N, K, ldb, 256 / cta_group))) return rc;
+  } else {
+    if ((rc = encode_operand(&tmA, A, M, K, lda, a_mn, 128))) return rc;
+    if ((rc = encode_operand(&tmB, Bm, N, K, ldb, b_mn, 256 / (cta_group * mcast)))) return rc;
+  }
   float* zero = nullptr;  // t' = 0 -> scale exp(0) * 1 = 1
   CK(cudaMalloc(reinterpret_cast<void**>(&zero), sizeof(float)));
   CK(cudaMemsetAsync(zero, 0, sizeof(float), st));
@@ -1547,7 +1592,7 @@ int siglip_debug_gemm_timed(int device, int cta_group, int M, int N, int K, cons
   p.prob[0].tiles_n = ceil_div(N, 256);
   p.prob[0].a_mn = a_mn ? 1 : 0;
   p.prob[0].b_mn = b_mn ? 1 : 0;
-  p.prob[0].ab_f16 = getenv("SIGLIP_DEBUG_AB_F16") ? 1 : 0;
+  p.prob[0].ab_f16 = fp8 ? 2 : (getenv("SIGLIP_DEBUG_AB_F16") ? 1 : 0);
   p.prob[0].acc_scale = 1.0f;
   p.prob[0].out = C;
   p.prob[0].ldo = ldc;

@@ -171,6 +171,9 @@ struct TileCoord {
   int prob;
   int m_blk;
   int n_blk;
+  int part;    // -1: whole tile; 0 .. sk_parts-1: this work item is one K-slice of a split tile (0 = the owner, which
+               // adds the other slices' partial accumulators and runs the epilogue)
+  int slot;    // split tiles only: index into the partial-accumulator workspace / arrival counters
 };
 
 // Work unit of a cluster: kMC vertically adjacent tiles (same n block, consecutive m blocks) — one per CTA (pair)
@@ -202,9 +205,20 @@ __device__ __forceinline__ int tile_cols(const Problem& pr, int n_blk) {
   }
 }
 
+// Work item -> tile. Items 0 .. sk_first-1 are whole tiles in schedule order; with split-K (out kernel, kMC == 1) the
+// remaining sk_tiles tiles — the ragged last wave — appear sk_parts times, slice-major, so that the slices of one tile
+// run on different clusters at the same time.
 template <int kMC>
 __device__ __forceinline__ TileCoord decode_tile(const KernelParams& p, int t, int mc_rank) {
   TileCoord c;
+  c.part = -1;
+  c.slot = 0;
+  if (kMC == 1 && p.sk_parts > 1 && t >= p.sk_first) {
+    const int q = t - p.sk_first;
+    c.part = q / p.sk_tiles;
+    c.slot = q - c.part * p.sk_tiles;
+    t = p.sk_first + c.slot;
+  }
   const int t0 = cluster_tiles<kMC>(p.prob[0]);
   c.prob = (t >= t0) ? 1 : 0;
   const int tt = c.prob ? t - t0 : t;
@@ -213,6 +227,18 @@ __device__ __forceinline__ TileCoord decode_tile(const KernelParams& p, int t, i
   c.m_blk = mrow * kMC + mc_rank;   // may be >= tiles_m for the last row when tiles_m is odd: fully masked tile
   c.n_blk = tt - mrow * tn;
   return c;
+}
+
+// k-blocks [kb0, kb1) of a work item: everything, or the item's slice of a split tile
+__device__ __forceinline__ void item_k_range(const KernelParams& p, const TileCoord& tc, int num_kb, int& kb0,
+                                             int& kb1) {
+  if (tc.part < 0) {
+    kb0 = 0;
+    kb1 = num_kb;
+  } else {
+    kb0 = static_cast<int>(static_cast<long long>(num_kb) * tc.part / p.sk_parts);
+    kb1 = static_cast<int>(static_cast<long long>(num_kb) * (tc.part + 1) / p.sk_parts);
+  }
 }
 
 // -------------------------------------------------------------------------------------------------
@@ -445,7 +471,8 @@ siglip_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_consta
   constexpr uint16_t kMcMask = static_cast<uint16_t>((1u << kClusterSize) - 1u);  // every CTA of the cluster
   const int cluster_id = blockIdx.x / kClusterSize;
   const int num_clusters = gridDim.x / kClusterSize;
-  const int total_tiles = cluster_tiles<kMC>(p.prob[0]) + (p.nprob > 1 ? cluster_tiles<kMC>(p.prob[1]) : 0);
+  const int whole_tiles = cluster_tiles<kMC>(p.prob[0]) + (p.nprob > 1 ? cluster_tiles<kMC>(p.prob[1]) : 0);
+  const int total_tiles = (kMC == 1 && p.sk_parts > 1) ? p.sk_first + p.sk_tiles * p.sk_parts : whole_tiles;
 
   if (warp == kProducerWarp && lane == 0) {
     prefetch_tmap(&tmA0);
@@ -506,9 +533,13 @@ siglip_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_consta
         const int b_rows = n_cur / kCG;                               // B rows this CTA holds for the tile
         const int n_idx = tc.n_blk * tile_stride_n<kMode, kMC>(pr) + static_cast<int>(cta_rank) * b_rows;
         const uint32_t stage_tx = static_cast<uint32_t>(C::kABytes + b_rows * kBlockK * 2) * kCG;
-        const int num_kb = (pr.K + kBlockK - 1) / kBlockK;
+        // elements per 128-byte swizzle row: 64 16-bit values, or 128 8-bit ones (fp8 experiment, K-major only)
+        const int kblk = (pr.ab_f16 == 2) ? 2 * kBlockK : kBlockK;
+        const int num_kb = (pr.K + kblk - 1) / kblk;
         const int a_mn = pr.a_mn, b_mn = pr.b_mn;
-        for (int kb = 0; kb < num_kb; ++kb) {
+        int kb0, kb1;
+        item_k_range(p, tc, num_kb, kb0, kb1);
+        for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(empty_bar(stage), phase ^ 1u, p.dbg, 1, t, kb, 0, p.wait_stats ? &w_empty : nullptr);
           if (elect_one_sync()) {
             const uint32_t sA = smem_base + stage * C::kStageBytes;
@@ -517,7 +548,7 @@ siglip_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_consta
             if (cta_rank == 0) mbar_arrive_expect_tx(fb, stage_tx);
             const uint32_t fb_local = fb;
             if constexpr (kCG == 2) fb = mapa_shared(fb, leader_rank);   // the pair's leader owns the full barriers
-            const int k_idx = kb * kBlockK;
+            const int k_idx = kb * kblk;
             if (!a_mn) {
               tma_load_2d_hint<kCG>(tmA, fb, sA, k_idx, m_idx, pol_a);  // box {64 k, 128 rows}
             } else {
@@ -592,11 +623,14 @@ siglip_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_consta
         // descriptors of stage 0; later stages add stage * kStageBytes >> 4 to the start-address field
         const uint64_t adesc0 = make_smem_desc_sw128(smem_base, a_lbo, 1024u);
         const uint64_t bdesc0 = make_smem_desc_sw128(smem_base + C::kABytes, b_lbo, 1024u);
-        const int num_kb = (pr.K + kBlockK - 1) / kBlockK;
+        const bool fp8 = (pr.ab_f16 == 2);
+        const int num_kb = (pr.K + (fp8 ? 2 * kBlockK : kBlockK) - 1) / (fp8 ? 2 * kBlockK : kBlockK);
+        int kb0, kb1;
+        item_k_range(p, tc, num_kb, kb0, kb1);
         mbar_wait(tmem_empty_bar(as), aphase ^ 1u, p.dbg, 2, t, as, 0, prof ? &w_tmem : nullptr);
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(as * kTileN);
-        for (int kb = 0; kb < num_kb; ++kb) {
+        for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(full_bar(stage), phase, p.dbg, 3, t, kb, 0, prof ? &w_full : nullptr);
           tc_fence_after();
           const long long c0 = prof ? clock_cycles() : 0;
@@ -604,10 +638,20 @@ siglip_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_consta
           if (elect_one_sync()) {
             const uint64_t adesc = adesc0 + static_cast<uint64_t>(stage * (C::kStageBytes >> 4));
             const uint64_t bdesc = bdesc0 + static_cast<uint64_t>(stage * (C::kStageBytes >> 4));
+            if (!fp8) {
 #pragma unroll
-            for (int k = 0; k < kBlockK / kUmmaK; ++k) {
-              umma_bf16<kCG>(tmem_d, adesc + static_cast<uint64_t>(k * a_adv),
-                             bdesc + static_cast<uint64_t>(k * b_adv), idesc, static_cast<uint32_t>((kb | k) != 0));
+              for (int k = 0; k < kBlockK / kUmmaK; ++k) {
+                umma_bf16<kCG>(tmem_d, adesc + static_cast<uint64_t>(k * a_adv),
+                               bdesc + static_cast<uint64_t>(k * b_adv), idesc,
+                               static_cast<uint32_t>(kb != kb0 || k != 0));
+              }
+            } else {   // kind::f8f6f4: 32 e4m3 values (32 bytes) per instruction along K — same byte geometry
+#pragma unroll
+              for (int k = 0; k < kBlockK / kUmmaK; ++k) {
+                umma_f8<kCG>(tmem_d, adesc + static_cast<uint64_t>(k * a_adv),
+                             bdesc + static_cast<uint64_t>(k * b_adv), idesc,
+                             static_cast<uint32_t>(kb != kb0 || k != 0));
+              }
             }
             c1 = prof ? clock_cycles() : 0;
             if constexpr (kMC > 1 && kCG == 1) {
@@ -617,7 +661,7 @@ siglip_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_consta
             } else {
               umma_commit<kCG>(empty_bar(stage));  // frees the smem stage (both CTAs) when the MMAs retire
             }
-            if (kb == num_kb - 1) {                // accumulator ready for the epilogue warps of this pair
+            if (kb == kb1 - 1) {                   // accumulator ready for the epilogue warps of this pair
               if constexpr (kMC > 1 && kCG == 2) {
                 umma_commit_2sm_mask(tmem_full_bar(as), static_cast<uint16_t>(0x3u << leader_rank));
               } else {
@@ -747,7 +791,7 @@ siglip_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_consta
         }
       }
 
-      auto slab = [&](const uint32_t(&v)[32], int c) {
+      auto slab = [&](uint32_t(&v)[32], int c) {
         const int col0 = col_base + c * 32;
         if constexpr (kMode == kModeLoss) {
           const bool sg = p.store_g != 0;
@@ -770,9 +814,73 @@ siglip_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_consta
             loss_slab<false, true, true>(v, t_eff, bias, row, col0, pr.M, pr.N, sg, gst, p.g_scale, p.g_diag, acc_sp, acc_g, acc_gs);
           }
         } else {
-          out_slab(v, scale, row, col0, pr, fix);
+          if (tc.part < 0) {
+            out_slab(v, scale, row, col0, pr, fix);
+          } else {
+            // split tile: 32x32 fp32 slab of this thread's row <-> workspace, lanes contiguous (512 B per warp access)
+            const int slab_id = cgrp * kSlabsPerWarp + c;
+            float4* ws = reinterpret_cast<float4*>(p.sk_ws) +
+                         ((static_cast<size_t>(tc.slot) * (p.sk_parts - 1)) * kCG + cta_rank) * (8 * 8 * kBlockM) +
+                         static_cast<size_t>(slab_id) * (8 * kBlockM) + row_in_cta;
+            const size_t part_stride = static_cast<size_t>(kCG) * (8 * 8 * kBlockM);   // float4 per slice
+            if (tc.part > 0) {
+              float4* dst = ws + static_cast<size_t>(tc.part - 1) * part_stride;
+#pragma unroll
+              for (int j4 = 0; j4 < 8; ++j4)
+                dst[j4 * kBlockM] = make_float4(__uint_as_float(v[4 * j4]), __uint_as_float(v[4 * j4 + 1]),
+                                                __uint_as_float(v[4 * j4 + 2]), __uint_as_float(v[4 * j4 + 3]));
+            } else {
+#pragma unroll 1
+              for (int sp = 0; sp < p.sk_parts - 1; ++sp) {     // fixed order: slice 0 (mine) + 1 + 2 + ...
+                const float4* src = ws + static_cast<size_t>(sp) * part_stride;
+#pragma unroll
+                for (int j4 = 0; j4 < 8; ++j4) {
+                  const float4 a = __ldcg(src + j4 * kBlockM);
+                  v[4 * j4] = __float_as_uint(__uint_as_float(v[4 * j4]) + a.x);
+                  v[4 * j4 + 1] = __float_as_uint(__uint_as_float(v[4 * j4 + 1]) + a.y);
+                  v[4 * j4 + 2] = __float_as_uint(__uint_as_float(v[4 * j4 + 2]) + a.z);
+                  v[4 * j4 + 3] = __float_as_uint(__uint_as_float(v[4 * j4 + 3]) + a.w);
+                }
+              }
+              out_slab(v, scale, row, col0, pr, fix);
+            }
+          }
         }
       };
+      if constexpr (kMode == kModeOut) {
+        if (tc.part == 0) {
+          // owner slice: the other slices' partial accumulators must be in the workspace (they run at the same time
+          // on other clusters and wait for nothing, so this cannot deadlock on a co-resident persistent grid)
+          if (lane == 0) {
+            const unsigned int need = static_cast<unsigned int>((p.sk_parts - 1) * kCG * kNumEpiWarps);
+            const unsigned int* ctr = p.sk_counters + 2 * tc.slot;
+            uint64_t t0 = 0;
+            uint32_t spins = 0;
+            while (true) {
+              unsigned int cv;
+              asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(cv) : "l"(ctr) : "memory");
+              if (cv >= need) break;
+              __nanosleep(100);
+              if ((++spins & 0x3ffu) == 0) {
+                const uint64_t now = globaltimer_ns();
+                if (t0 == 0) t0 = now;
+                if (now - t0 > SIGLIP_WAIT_TIMEOUT_NS) {
+                  if (p.dbg != nullptr) {
+                    p.dbg->block = blockIdx.x;
+                    p.dbg->thread = threadIdx.x;
+                    p.dbg->aux0 = cv;
+                    p.dbg->aux1 = need;
+                    p.dbg->code = 4;
+                    __threadfence_system();
+                  }
+                  __trap();
+                }
+              }
+            }
+          }
+          __syncwarp();
+        }
+      }
 
       // kSlabsPerWarp slabs of 32 columns. With four epilogue warps per SM sub-partition the TMEM load latency
       // of one warp is covered by the arithmetic of the others.
@@ -804,6 +912,23 @@ siglip_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_consta
         kahan_add(s_sp, c_sp, acc_sp);
         kahan_add(s_g, c_g, acc_g);
         kahan_add(s_gs, c_gs, acc_gs);
+      } else {
+        if (tc.part > 0) {
+          // my slabs of the partial accumulator are written: arrive (release) on the tile's counter
+          __threadfence();
+          __syncwarp();
+          if (lane == 0) atomicAdd(p.sk_counters + 2 * tc.slot, 1u);
+        } else if (tc.part == 0) {
+          // every owner warp has consumed the partials: the last one re-arms the counters for the next launch
+          __syncwarp();
+          if (lane == 0) {
+            const unsigned int seen = atomicAdd(p.sk_counters + 2 * tc.slot + 1, 1u);
+            if (seen == static_cast<unsigned int>(kCG * kNumEpiWarps) - 1u) {
+              p.sk_counters[2 * tc.slot] = 0u;
+              p.sk_counters[2 * tc.slot + 1] = 0u;
+            }
+          }
+        }
       }
       if (++as == kAccStages) {
         as = 0;
@@ -1314,10 +1439,34 @@ int launch_impl(const CUtensorMap* tmA0, const CUtensorMap* tmB0, const CUtensor
     if (getenv("SIGLIP_DEBUG_WAITSTATS")) printf("[launch] cluster size %d: %d co-resident clusters\n", kClusterSize, n);
   }
   int clusters = max_clusters < num_sms / kClusterSize ? max_clusters : num_sms / kClusterSize;
+  KernelParams pl = p;
+  pl.sk_parts = 0;
+  if (kMode == kModeOut && kMC == 1 && p.sk_request != 0 && p.sk_ws != nullptr && clusters > 1) {
+    // Split-K of the ragged last wave: `rem` tiles left after the full waves would occupy rem of `clusters` units for
+    // a whole tile time. Cut each of them into S = floor(clusters / rem) K-slices (S * rem <= clusters work items, one
+    // per unit): the last wave then lasts ~1/S of a tile. Not worth it when the last wave is more than half full
+    // (S would be 1) or the slices get shorter than a handful of k-blocks.
+    const int rem = total_tiles % clusters;
+    const int min_k = pl.prob[0].K < pl.prob[pl.nprob > 1 ? 1 : 0].K ? pl.prob[0].K : pl.prob[pl.nprob > 1 ? 1 : 0].K;
+    const int num_kb = (min_k + kBlockK - 1) / kBlockK;
+    if (rem > 0) {
+      int S = clusters / rem;
+      if (p.sk_request > 1 && S > p.sk_request) S = p.sk_request;
+      if (p.sk_request < 0 && S > 4) S = 4;
+      while (S > 1 && num_kb / S < 8) --S;
+      const size_t need = static_cast<size_t>(rem) * (S - 1) * kCG * (8 * 8 * kBlockM) * sizeof(float4);
+      if (S >= 2 && rem <= p.sk_max_tiles && need <= p.sk_ws_bytes) {
+        pl.sk_parts = S;
+        pl.sk_tiles = rem;
+        pl.sk_first = total_tiles - rem;
+        total_tiles = pl.sk_first + rem * S;
+      }
+    }
+  }
   if (clusters > total_tiles) clusters = total_tiles;
   if (clusters < 1) clusters = 1;
   cfg.gridDim = dim3(clusters * kClusterSize);
-  e = cudaLaunchKernelEx(&cfg, kern, *tmA0, *tmB0, *tmA1, *tmB1, *tmG, p);
+  e = cudaLaunchKernelEx(&cfg, kern, *tmA0, *tmB0, *tmA1, *tmB1, *tmG, pl);
   return static_cast<int>(e);
 }
 

@@ -18,7 +18,8 @@ struct Problem {
   int tiles_m, tiles_n;
   int tile_n;       // out kernel, N-major B: 128 = narrow column tiles (tiles_n = ceil(N / 128)); 0 / 256 = default
   int a_mn, b_mn;
-  int ab_f16;       // both operands are IEEE fp16 (gradient contractions: scaled sigma operand x scaled embeddings)
+  int ab_f16;       // 0: bf16 operands; 1: both IEEE fp16 (gradient contractions: scaled sigma x scaled embeddings);
+                    // 2: both fp8 e4m3, K-major only (kind::f8f6f4 — the SURVEY.md §8f-4 measurement, siglip_debug_gemm)
   float acc_scale;  // multiplies the accumulator in the out epilogue (2^-k for a 2^k-scaled fp16 A operand)
   // epilogue of the "out" kernel:
   //   out = scale * (acc * acc_scale + fix_vec[row] * fix_mat[row, col]) (+ add_src[row, col]); fp32 or bf16 output
@@ -105,6 +106,17 @@ struct KernelParams {
   // out kernel, problem 1: do not read add_src before this local flag (set by an aux job's done_flag) holds done_value
   const volatile unsigned int* p1_wait_flag;
   unsigned int p1_wait_value;
+  // Split-K of the ragged last wave (out kernel, no multicast): work items [sk_first, sk_first + sk_tiles * sk_parts)
+  // are K-slices of the last sk_tiles tiles; slice 0 owns the tile: it waits for the others' fp32 partial accumulators
+  // in sk_ws and adds them in slice order (bitwise independent of timing).
+  int sk_parts;                // 0 / 1 = off
+  int sk_first;
+  int sk_tiles;
+  int sk_request;              // host request to launch_gemm: -1 choose, 0 off, S >= 2
+  float* sk_ws;                // [sk_tiles][sk_parts - 1][cta_group][8 slabs][8][128] float4
+  size_t sk_ws_bytes;
+  unsigned int* sk_counters;   // [sk_tiles][2]: arrivals of the non-owner warps, owner warps that consumed them
+  int sk_max_tiles;            // capacity of sk_counters
   unsigned long long peer_timeout_ns;  // bound of every wait on a peer flag (a dead peer traps instead of hanging)
   unsigned long long* aux_trace;       // optional [4] globaltimer stamps of CTA 0's aux thread: start, flags seen, jobs done
 };

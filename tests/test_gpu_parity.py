@@ -773,6 +773,7 @@ def test_gradient_column_tile_width_does_not_change_the_result(shape, cg):
     img, txt = _synth(B, D, seed=11)
     tp, b = _scal(math.log(10.0)), _scal(-10.0)
     eng = _engine(B, D, cg)
+    eng.set_option(_capi.SIGLIP_OPT_SPLIT_K, 0)     # split-K regroups the K sum per tile shape (tested separately)
     out = {}
     for tn in (256, 128, 0):
         eng.set_option(_capi.SIGLIP_OPT_GRAD_TILE_N, tn)
@@ -1003,9 +1004,11 @@ def test_module_accepts_any_embedding_width_and_views():
         loss.backward()
         torch.cuda.synchronize()
         assert a.grad.shape == (B, D) and b.grad.shape == (B, D)
+        # fp32 leaves -> fp16(16 x) operands (11 significant bits); at D = 2 nothing averages the rounding of a single
+        # operand element, so the element-wise bound is looser than the matrix-level one
         _check(f"D={D} loss", loss.detach(), ref["loss"])
-        _check(f"D={D} dimg", a.grad, ref["dimg"])
-        _check(f"D={D} dtxt", b.grad, ref["dtxt_chunks"][0])
+        _check(f"D={D} dimg", a.grad, ref["dimg"], max_tol=4e-3)
+        _check(f"D={D} dtxt", b.grad, ref["dtxt_chunks"][0], max_tol=4e-3)
     # a misaligned, strided view of a larger bf16 buffer
     D = 64
     big = torch.nn.functional.normalize(torch.randn(B, 2 * D + 3, device=_dev())).to(torch.bfloat16)
@@ -1083,3 +1086,62 @@ def test_peer_timeout_option_and_trace_hook():
     for (t0, tflag, tdone, tend) in tr:
         assert t0 > 0 and tdone >= t0 and (tend == 0 or tend >= t0)
     eng.close()
+
+
+# ---------------------------------------------------------------------------------------------------------
+# split-K of the gradient kernel's ragged last wave; fp8 (kind::f8f6f4) measurement path
+# ---------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("shape", [(4096, 768), (1000, 136), (2048, 1152), (520, 264), (8192, 768)])
+@pytest.mark.parametrize("cg", [1, 2])
+def test_split_k_is_deterministic_and_matches_unsplit(shape, cg):
+    """SIGLIP_OPT_SPLIT_K: the tiles of a ragged last wave are cut into K-slices whose fp32 partial accumulators meet in
+    a workspace and are added in slice order — bitwise repeatable, and equal to the unsplit result up to fp32
+    summation order."""
+    from distributed_sigmoid_loss_b200 import _capi
+    B, D = shape
+    img, txt = _synth(B, D, seed=13)
+    tp, b = _scal(math.log(10.0)), _scal(-10.0)
+    eng = _engine(B, D, cg)
+    out = {}
+    for sk in (0, -1, 2, 3):
+        eng.set_option(_capi.SIGLIP_OPT_SPLIT_K, sk)
+        runs = []
+        for _ in range(2):
+            _, dimg, dtxt, _, _ = eng.fwd_bwd(img, txt, tp, b)
+            torch.cuda.synchronize()
+            runs.append((dimg.clone(), dtxt.clone()))
+        assert torch.equal(runs[0][0], runs[1][0]) and torch.equal(runs[0][1], runs[1][1])
+        out[sk] = runs[0]
+    for sk in (-1, 2, 3):
+        _check(f"dimg split {sk}", out[sk][0], out[0][0], tol=2e-6)
+        _check(f"dtxt split {sk}", out[sk][1], out[0][1], tol=2e-6)
+    with pytest.raises(RuntimeError):
+        eng.set_option(_capi.SIGLIP_OPT_SPLIT_K, 1)
+    eng.close()
+
+
+@pytest.mark.parametrize("cg", [1, 2])
+def test_fp8_measurement_path_computes_the_e4m3_product(cg, monkeypatch):
+    """siglip_debug_gemm under SIGLIP_DEBUG_AB_FP8: e4m3 x e4m3 -> fp32 on the same mainloop (tcgen05 kind::f8f6f4).
+    Products of e4m3 values are exact in fp32, so the result equals the fp32 product of the dequantised operands."""
+    from distributed_sigmoid_loss_b200 import _capi
+    L = _capi.lib()
+    monkeypatch.setenv("SIGLIP_DEBUG_AB_FP8", "1")
+    monkeypatch.delenv("SIGLIP_DEBUG_AB_F16", raising=False)
+    monkeypatch.delenv("SIGLIP_DEBUG_MCAST", raising=False)
+    torch.manual_seed(2)
+    for (M, N, K) in [(256, 256, 128), (512, 768, 1024), (300, 264, 400)]:
+        A = torch.randn(M, K, device=_dev()).to(torch.float8_e4m3fn)
+        Bm = torch.randn(N, K, device=_dev()).to(torch.float8_e4m3fn)
+        ld = (K + 15) // 16 * 16
+        Ab = torch.zeros(M, ld, device=_dev(), dtype=torch.uint8)
+        Bb = torch.zeros(N, ld, device=_dev(), dtype=torch.uint8)
+        Ab[:, :K] = A.view(torch.uint8)
+        Bb[:, :K] = Bm.view(torch.uint8)
+        C = torch.full((M, N), float("nan"), device=_dev())
+        rc = L.siglip_debug_gemm(0, cg, M, N, K, Ab.data_ptr(), ld, 0, Bb.data_ptr(), ld, 0, C.data_ptr(), N,
+                                 torch.cuda.current_stream().cuda_stream)
+        assert rc == 0, _capi.last_error()
+        torch.cuda.synchronize()
+        ref = A.float() @ Bm.float().T
+        assert float((C - ref).abs().max()) <= 1e-5 * float(ref.abs().max()) * math.sqrt(K) + 1e-4
