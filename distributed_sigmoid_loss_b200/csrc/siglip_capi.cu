@@ -1000,6 +1000,8 @@ static int ctx_create_impl(siglip_ctx** out, int device, int rank, int world, co
   c->dbg_no_gstore = getenv("SIGLIP_DEBUG_NO_GSTORE") != nullptr;
   c->dbg_no_cvt = getenv("SIGLIP_DEBUG_NO_CVT") != nullptr;
   c->dbg_loss_waitstats = getenv("SIGLIP_DEBUG_LOSS_WAITSTATS") != nullptr;
+  if (const char* e = getenv("SIGLIP_INKERNEL_SYNC")) c->inkernel_sync = atoi(e) ? 1 : 0;   // A/B measurements
+  if (const char* e = getenv("SIGLIP_SPLIT_K")) c->split_k = atoi(e);
   if (const char* e = getenv("SIGLIP_PEER_TIMEOUT_MS")) {
     const long long v = atoll(e);
     if (v > 0) c->peer_timeout_ms = v;

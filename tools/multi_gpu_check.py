@@ -80,17 +80,47 @@ def main() -> int:
                 dtxt=rel_f(dtxt.cpu(), torch.from_numpy(ref["dtxt"])),
                 dtp=abs(float(dtp) - ref["dt_prime"]) / abs(ref["dt_prime"]),
                 db=abs(float(db) - ref["dbias"]) / abs(ref["dbias"])))
-        # module surface + overlap_pull off (separate copy) must agree too
-        eng.set_option(_capi.SIGLIP_OPT_OVERLAP_PULL, 0)
-        a, b = img.clone().requires_grad_(True), txt.clone().requires_grad_(True)
-        l2 = mod(a, b)
-        l2.backward()
-        torch.cuda.synchronize()
-        report(f"module/no-overlap B={B}", dict(
-            loss=abs(float(l2) - ref["loss"]) / abs(ref["loss"]),
-            dimg=rel_f(a.grad.float().cpu(), torch.from_numpy(ref["dimg"])),
-            dtxt=rel_f(b.grad.float().cpu(), torch.from_numpy(ref["dtxt"]))), tol=4e-3)
-        eng.set_option(_capi.SIGLIP_OPT_OVERLAP_PULL, 1)
+        # the split forward / backward API (one sigma operand per chunk, helper-kernel flags) on the same peers
+        tpt, bt = torch.tensor([tp], device=dev), torch.tensor([bias], device=dev)
+        for rep in range(2):
+            ls = eng.forward(img, txt, tpt, bt, True)
+            dimg_s, dtxt_s, dtp_s, db_s = eng.backward(img, txt, tpt, None)
+            torch.cuda.synchronize()
+            report(f"split API B={B} D={D} rep{rep}", dict(
+                loss=abs(float(ls) - ref["loss"]) / abs(ref["loss"]),
+                dimg=rel_f(dimg_s.cpu(), torch.from_numpy(ref["dimg"])),
+                dtxt=rel_f(dtxt_s.cpu(), torch.from_numpy(ref["dtxt"])),
+                dtp=abs(float(dtp_s) - ref["dt_prime"]) / abs(ref["dt_prime"]),
+                db=abs(float(db_s) - ref["dbias"]) / abs(ref["dbias"]),
+                vs_fused_dtxt=rel_f(dtxt_s, dtxt)), tol=1e-3)
+        # the fused step with the flags handled by separate helper kernels (SIGLIP_OPT_INKERNEL_SYNC = 0)
+        eng.set_option(_capi.SIGLIP_OPT_INKERNEL_SYNC, 0)
+        for rep in range(2):
+            l0, dimg0, dtxt0, dtp0, db0 = eng.fwd_bwd(img, txt, tpt, bt)
+            torch.cuda.synchronize()
+            report(f"fused, helper-kernel flags B={B} rep{rep}", dict(
+                loss=abs(float(l0) - ref["loss"]) / abs(ref["loss"]),
+                dimg=rel_f(dimg0.cpu(), torch.from_numpy(ref["dimg"])),
+                dtxt=rel_f(dtxt0.cpu(), torch.from_numpy(ref["dtxt"])),
+                bitwise_vs_inkernel=0.0 if (torch.equal(dimg0, dimg) and torch.equal(dtxt0, dtxt)) else 1.0))
+        eng.set_option(_capi.SIGLIP_OPT_INKERNEL_SYNC, 1)
+        # module surface (fused schedule by default on a multi-rank group; split schedule on request)
+        for fused in (None, False):
+            modx = DDPSigmoidLoss(B, fused_step=fused).to(dev)
+            with torch.no_grad():
+                modx.t_prime.fill_(tp)
+                modx.bias.fill_(bias)
+            a, b = img.clone().requires_grad_(True), txt.clone().requires_grad_(True)
+            l2 = modx(a, b)
+            l2.backward()
+            torch.cuda.synchronize()
+            report(f"module fused_step={fused} B={B}", dict(
+                loss=abs(float(l2) - ref["loss"]) / abs(ref["loss"]),
+                dimg=rel_f(a.grad.float().cpu(), torch.from_numpy(ref["dimg"])),
+                dtxt=rel_f(b.grad.float().cpu(), torch.from_numpy(ref["dtxt"])),
+                dtp=abs(float(modx.t_prime.grad) - ref["dt_prime"]) / abs(ref["dt_prime"]),
+                db=abs(float(modx.bias.grad) - ref["dbias"]) / abs(ref["dbias"])), tol=4e-3)
+            del modx
 
     # ---- fp32 callers: raw fp32 inputs -> fp16(16 x) operands, text chunks exchanged in that format ---------------
     if not args.skip_parity:
@@ -113,6 +143,49 @@ def main() -> int:
                 dtxt=rel_f(b.grad.cpu(), torch.from_numpy(ref["dtxt"])),
                 dtp=abs(float(mod.t_prime.grad) - ref["dt_prime"]) / abs(ref["dt_prime"]),
                 db=abs(float(mod.bias.grad) - ref["dbias"]) / abs(ref["dbias"])))
+
+    # ---- ranks with different batch sizes (B_r = 72 + 24 r), float64 closed form over the global set ----
+    if not args.skip_parity:
+        from distributed_sigmoid_loss_b200 import SigmoidLossEngine
+        Bs = [72 + 24 * r for r in range(world)]
+        D, tp, bias = 136, math.log(10.0), -9.0
+        g = torch.Generator().manual_seed(321)
+        imgs = [torch.nn.functional.normalize(torch.randn(b, D, generator=g)).to(torch.bfloat16) for b in Bs]
+        txts = [torch.nn.functional.normalize(torch.randn(b, D, generator=g)).to(torch.bfloat16) for b in Bs]
+        t = math.exp(tp)
+        i64 = imgs[rank].double()
+        loss_ref, dimg_ref, dtp_ref, db_ref = 0.0, torch.zeros_like(i64), 0.0, 0.0
+        for c in range(world):
+            s_ = i64 @ txts[c].double().T
+            z = t * s_ + bias
+            y = -torch.ones_like(z)
+            if c == rank:
+                y.fill_diagonal_(1.0)
+            gmat = -y * torch.sigmoid(-y * z) / Bs[rank]
+            loss_ref += float(torch.nn.functional.softplus(-y * z).sum() / Bs[rank])
+            dimg_ref += t * (gmat @ txts[c].double())
+            dtp_ref += float(t * (gmat * s_).sum())
+            db_ref += float(gmat.sum())
+        # text gradient of MY chunk: sum over all ranks r of t * G_{r,me}^T img_r
+        dtxt_ref = torch.zeros(Bs[rank], D, dtype=torch.float64)
+        for r in range(world):
+            s_ = imgs[r].double() @ txts[rank].double().T
+            z = t * s_ + bias
+            y = -torch.ones_like(z)
+            if r == rank:
+                y.fill_diagonal_(1.0)
+            gmat = -y * torch.sigmoid(-y * z) / Bs[r]
+            dtxt_ref += t * (gmat.T @ imgs[r].double())
+        engu = SigmoidLossEngine(Bs[rank], D, dev, batch_per_rank=Bs)
+        tpt, bt = torch.tensor([tp], device=dev), torch.tensor([bias], device=dev)
+        for rep in range(2):
+            lu, dimg_u, dtxt_u, dtp_u, db_u = engu.fwd_bwd(imgs[rank].to(dev), txts[rank].to(dev), tpt, bt)
+            torch.cuda.synchronize()
+            report(f"uneven batches {Bs} rep{rep}", dict(
+                loss=abs(float(lu) - loss_ref) / abs(loss_ref), dimg=rel_f(dimg_u.cpu(), dimg_ref),
+                dtxt=rel_f(dtxt_u.cpu(), dtxt_ref), dtp=abs(float(dtp_u) - dtp_ref) / abs(dtp_ref),
+                db=abs(float(db_u) - db_ref) / abs(db_ref)))
+        engu.close()
 
     # ---- larger: fp32 autograd; dtxt reference summed over ranks ------------------------------------------
     B, D, tp, bias = 2048, 768, math.log(10.0), -10.0
