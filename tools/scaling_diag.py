@@ -166,6 +166,31 @@ def main() -> int:
     if "C" in args.phases and world > 1:
         eng = SigmoidLossEngine(B, D, dev)
         run(eng, "C coupled W=N", True)
+        if "T" in args.phases:
+            # in-kernel timeline of the auxiliary warps (CTA 0) for three coupled steps: how long they wait for peer
+            # flags, how long the pulls / folds take, and how much of the kernel is left after them
+            eng.set_option(_capi.SIGLIP_OPT_AUX_TRACE, 1)
+            for _ in range(3):
+                eng.fwd_bwd(img, txt, tp, bt, torch.bfloat16)
+            tr = eng.aux_trace()
+            eng.set_option(_capi.SIGLIP_OPT_AUX_TRACE, 0)
+            rows = []
+            for (t0, tflag, tdone, tend) in tr[-2 * world:]:          # the last step: L0 L1 G1 ... G0
+                wait_us = (tflag - t0) / 1e3 if tflag else 0.0
+                jobs_us = (tdone - (tflag if tflag else t0)) / 1e3
+                kern_us = (tend - t0) / 1e3 if tend else float("nan")
+                rows.append((wait_us, jobs_us, kern_us))
+            tt = torch.tensor(rows, device=dev, dtype=torch.float64)
+            allr = [torch.empty_like(tt) for _ in range(world)]
+            dist.all_gather(allr, tt)
+            if rank == 0:
+                names = ["L0"] + [x for k in range(1, world) for x in (f"L{k}", f"G{k}")] + ["G0"]
+                print("== T aux-warp timeline of the last coupled step (us): wait for the last peer flag | time from there "
+                      "to jobs done | kernel (aux start -> last CTA done) ==", flush=True)
+                for r in range(world):
+                    print(f"  rank {r}: " + "  ".join(f"{n}:{w:.0f}|{j:.0f}|{k:.0f}" for n, (w, j, k) in
+                                                    zip(names, allr[r].tolist())), flush=True)
+                results["T trace"] = {"names": names, "per_rank": [a.tolist() for a in allr]}
         if "D" in args.phases:
             eng.set_option(_capi.SIGLIP_OPT_OVERLAP_REDUCE, 0)
             run(eng, "D coupled W=N, reduction at the end", True)
