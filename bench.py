@@ -411,7 +411,8 @@ def run_ours(args):
     img_h, txt_h = synth(rank, B, D)
     img = img_h.to(dev).requires_grad_(True)
     txt = txt_h.to(dev).requires_grad_(True)
-    mod = DDPSigmoidLoss(B, cta_group=args.cta_group).to(dev)
+    fused_step = {"auto": None, "fused": True, "split": False}[args.schedule]
+    mod = DDPSigmoidLoss(B, cta_group=args.cta_group, fused_step=fused_step).to(dev)
     eng = mod.engine_for(B, D, dev)
     tpt = torch.tensor([math.log(10.0)], device=dev)
     bt = torch.tensor([-10.0], device=dev)
@@ -475,7 +476,6 @@ def run_ours(args):
         if (warm_ms >= args.sustain_ms and stable) or warm_ms >= max(4000.0, args.sustain_ms):
             break
     barrier()
-    eng.set_option(_capi.SIGLIP_OPT_KERNEL_TIMING, 1)
     launches0 = eng.launch_count
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     # NVML queries take milliseconds: read the NVLink counters OUTSIDE the barrier-bracketed timed region (a late rank 0
@@ -499,9 +499,21 @@ def run_ours(args):
         ms_total = float(t)
     ms_step = ms_total / args.steps
     launches = eng.launch_count - launches0
+    value = W * B / (ms_step * 1e-3)
+    # Second timed region, right behind the first, same K steps: every loss / gradient launch bracketed by CUDA events on
+    # the launch stream (the per-kernel durations of the roofline). Kept apart from the value above because an event
+    # between two launches disables their programmatic dependent launch (set-up overlapping the previous tail).
+    eng.set_option(_capi.SIGLIP_OPT_KERNEL_TIMING, 1)
+    barrier()
+    k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    k0.record()
+    for _ in range(args.steps):
+        step()
+    k1.record()
+    barrier()
+    ms_step_events = k0.elapsed_time(k1) / args.steps
     loss_ms, loss_n, grad_ms, grad_n = eng.kernel_times()
     eng.set_option(_capi.SIGLIP_OPT_KERNEL_TIMING, 0)
-    value = W * B / (ms_step * 1e-3)
     per_rank = allgather_floats([ms_mine / args.steps, loss_ms / max(loss_n, 1), grad_ms / max(grad_n, 1),
                                  (loss_ms + grad_ms) / args.steps, my_clock if my_clock is not None else -1.0])
 
@@ -636,7 +648,10 @@ def run_ours(args):
                              if B >= 8192 else "no explicit flush: inputs + sigma operand of a step fit the 126 MB L2 at this "
                                                "shape (as they do in a training loop that calls the loss every step)",
                        "api": "DDPSigmoidLoss.forward + loss.backward() (torch autograd over the C ABI)"
-                              if args.api == "module" else "siglip_fwd_bwd (C ABI, one fused call, bf16 gradients)"},
+                              if args.api == "module" else "siglip_fwd_bwd (C ABI, one fused call, bf16 gradients)",
+                       "schedule": ("fused step: L0 L1 G1 ... G0, two sigma operands, cross-rank flags inside the kernels"
+                                    if (fused_step or (fused_step is None and W > 1) or args.api == "fused") else
+                                    "split: W loss kernels in forward(), W gradient kernels in backward()")},
             "loss": float(loss.detach().reshape(-1)[0]),
             "parity": parity,
             "flops_per_step_per_rank": 6.0 * B * (W * B) * D,
@@ -664,7 +679,10 @@ def run_ours(args):
             "roofline": {"bound": "tensor", "kernel": "siglip_gemm_kernel<cg,1> (dimg + dtxt contractions)",
                          "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                          "frac": (achieved / peak) if achieved else None, "peak_source": peak_src,
-                         "avg_launch_ms": grad_avg_ms, "launches_timed": grad_n, "traffic": traffic,
+                         "avg_launch_ms": grad_avg_ms, "launches_timed": grad_n,
+                         "timed_in": f"a second region of {args.steps} steps right behind the value's region, every launch "
+                                     f"bracketed by CUDA events on its stream: {ms_step_events:.4f} ms/step there on rank 0",
+                         "ms_per_step_with_kernel_events": ms_step_events, "traffic": traffic,
                          "traffic_source": traffic_src,
                          "loss_kernel": {"achieved": flops_loss / (loss_avg_ms * 1e-3) / 1e12 if loss_n else None,
                                          "avg_launch_ms": loss_avg_ms, "launches_timed": loss_n}},
@@ -733,6 +751,9 @@ def main():
     ap.add_argument("--dim", type=int, default=1024)
     ap.add_argument("--api", default="module", choices=["module", "fused"],
                     help="what one timed step calls: the nn.Module (forward + backward) or the fused C-ABI entry")
+    ap.add_argument("--schedule", default="auto", choices=["auto", "fused", "split"],
+                    help="module schedule: auto = fused step (two sigma operands, in-kernel flags) on a multi-rank group and "
+                         "split forward/backward on one rank; fused / split force one")
     ap.add_argument("--cta-group", type=int, default=int(os.environ.get("SIGLIP_CTA_GROUP", "2")))
     ap.add_argument("--cpu-steps", type=int, default=3, help="timed steps of the cpu_baseline leg inside the N=1 run")
     ap.add_argument("--no-cpu-baseline", action="store_true")

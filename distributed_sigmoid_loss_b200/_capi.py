@@ -77,6 +77,7 @@ SIGLIP_OPT_PEER_TIMEOUT_MS = 15
 SIGLIP_OPT_INKERNEL_SYNC = 16
 SIGLIP_OPT_SPLIT_K = 17
 SIGLIP_OPT_AUX_TRACE = 18
+SIGLIP_OPT_PDL = 19
 
 _lib: Optional[ctypes.CDLL] = None
 

@@ -172,6 +172,7 @@ struct siglip_ctx {
   int grad_tile_n = 0;                   // column-tile width of the gradient kernel: 0 = choose, 128, 256
   int input_f16 = 0;                     // img / txt are fp16(x * kXScale) instead of bf16 (fp32-input path)
   int saved_f16 = 0;                     // format of the embeddings of the forward saved for backward
+  int pdl = 1;                           // programmatic dependent launch of the tcgen05 kernels (set-up overlaps the previous tail)
   int inkernel_sync = 1;                 // fused step: flags waited for / raised inside the tcgen05 kernels (0: helper launches)
   int split_k = -1;                      // gradient kernel: -1 = choose, 0 = off, S >= 2 = split the tiles of a ragged last wave
   long long peer_timeout_ms = 600000;    // bound of every wait on a peer (10 min: a peer may be saving a checkpoint)
@@ -195,7 +196,7 @@ struct siglip_ctx {
   float* loop_mailboxes = nullptr;       // loopback only: [world][2] stand-ins for the peers' (dt', dbias) mailboxes
   float* loop_zero = nullptr;            // loopback only: [world][Bmax, D] zeros standing in for the peers' contribution slots
   float* scalars = nullptr;              // [24] device scalars: host API staging, saved dt'/dbias of the last forward
-  unsigned long long* aux_trace = nullptr;  // [kTraceLaunches][4] globaltimer stamps (SIGLIP_OPT_AUX_TRACE)
+  unsigned long long* aux_trace = nullptr;  // [kTraceLaunches][8] globaltimer stamps (SIGLIP_OPT_AUX_TRACE)
   float* splitk_ws = nullptr;            // fp32 partial accumulators of the split tiles of the gradient kernel
   unsigned int* splitk_counters = nullptr;  // per split tile: arrivals of the non-owner parts (monotonic)
   size_t splitk_ws_bytes = 0;
@@ -329,6 +330,7 @@ void apply_aux(siglip_ctx* c, KernelParams& p, const AuxList& aux, const EndSign
     if (p.aux[i].sig_n > 0 || p.aux[i].done_flag != nullptr) p.aux[i].ticket = c->sync_words + i;
   }
   p.cvt_scale = kXScale;
+  p.pdl = c->pdl;
   p.peer_timeout_ns = peer_timeout_ns(c);
   if (end.n > 0 || c->aux_trace_on) {
     p.end_sig_ptrs = end.ptrs;
@@ -337,7 +339,7 @@ void apply_aux(siglip_ctx* c, KernelParams& p, const AuxList& aux, const EndSign
     p.end_ticket = c->sync_words + kSyncEndTicket;
   }
   if (c->aux_trace_on && c->aux_trace != nullptr && c->aux_trace_n < kTraceLaunches) {
-    p.aux_trace = c->aux_trace + 4ull * c->aux_trace_n;
+    p.aux_trace = c->aux_trace + 8ull * c->aux_trace_n;
     c->aux_trace_n++;
   }
 }
@@ -1002,6 +1004,7 @@ static int ctx_create_impl(siglip_ctx** out, int device, int rank, int world, co
   c->dbg_loss_waitstats = getenv("SIGLIP_DEBUG_LOSS_WAITSTATS") != nullptr;
   if (const char* e = getenv("SIGLIP_INKERNEL_SYNC")) c->inkernel_sync = atoi(e) ? 1 : 0;   // A/B measurements
   if (const char* e = getenv("SIGLIP_SPLIT_K")) c->split_k = atoi(e);
+  if (const char* e = getenv("SIGLIP_PDL")) c->pdl = atoi(e) ? 1 : 0;
   if (const char* e = getenv("SIGLIP_PEER_TIMEOUT_MS")) {
     const long long v = atoll(e);
     if (v > 0) c->peer_timeout_ms = v;
@@ -1125,14 +1128,17 @@ int siglip_ctx_set_option(siglip_ctx* c, int option, int value) {
       if (value < -1 || value == 1 || value > 8) return fail(SIGLIP_ERR_INVALID, "split_k must be -1 (auto), 0 (off) or 2..8");
       c->split_k = value;
       return 0;
+    case SIGLIP_OPT_PDL:
+      c->pdl = value ? 1 : 0;
+      return 0;
     case SIGLIP_OPT_AUX_TRACE:
       c->aux_trace_on = value ? 1 : 0;
       c->aux_trace_n = 0;
       if (value && c->aux_trace == nullptr) {
         CK(cudaSetDevice(c->device));
-        CK(cudaMalloc(reinterpret_cast<void**>(&c->aux_trace), kTraceLaunches * 4 * sizeof(unsigned long long)));
+        CK(cudaMalloc(reinterpret_cast<void**>(&c->aux_trace), kTraceLaunches * 8 * sizeof(unsigned long long)));
       }
-      if (value) CK(cudaMemset(c->aux_trace, 0, kTraceLaunches * 4 * sizeof(unsigned long long)));
+      if (value) CK(cudaMemset(c->aux_trace, 0, kTraceLaunches * 8 * sizeof(unsigned long long)));
       return 0;
     default:
       return fail(SIGLIP_ERR_INVALID, "unknown option");
@@ -1488,7 +1494,7 @@ int siglip_ctx_aux_trace(siglip_ctx* c, unsigned long long* out, int max_launche
   CK(cudaDeviceSynchronize());
   int n = static_cast<int>(c->aux_trace_n);
   if (n > max_launches) n = max_launches;
-  if (n > 0) CK(cudaMemcpy(out, c->aux_trace, static_cast<size_t>(n) * 4 * sizeof(unsigned long long),
+  if (n > 0) CK(cudaMemcpy(out, c->aux_trace, static_cast<size_t>(n) * 8 * sizeof(unsigned long long),
                            cudaMemcpyDeviceToHost));
   *n_launches = n;
   c->aux_trace_n = 0;

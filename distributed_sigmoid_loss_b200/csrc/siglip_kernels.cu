@@ -381,6 +381,9 @@ __device__ __forceinline__ void loss_slab(const uint32_t (&v)[32], float t, floa
 
 // Epilogue of the out kernel: one 32-column slab.
 //   val = scale * (acc * acc_scale + fix * x[row, col]) (+ add_src[row, col]);  written as fp32 or bf16
+// Every global load of the slab is issued before the first store: the stores may alias the loads as far as the compiler
+// knows, and a load -> store -> load -> store chain (8 exposed L2 round trips per warp and tile) was most of the 15 us
+// between the last MMA and the end of the kernel.
 __device__ __forceinline__ void out_slab(const uint32_t (&v)[32], float scale, int row, int col0, const Problem& pr,
                                          float fix) {
   if (row >= pr.M) return;
@@ -390,47 +393,58 @@ __device__ __forceinline__ void out_slab(const uint32_t (&v)[32], float scale, i
   const __nv_bfloat16* xrow = pr.fix_mat ? pr.fix_mat + static_cast<long long>(row) * pr.ldx : nullptr;
   const float* arow = pr.add_src ? pr.add_src + static_cast<long long>(row) * pr.ld_add : nullptr;
 #pragma unroll
-  for (int q = 0; q < 4; ++q) {       // 8 columns at a time (N % 8 == 0 is enforced by the host)
-    const int c = col0 + 8 * q;
-    if (c < pr.N) {
-      float o[8];
+  for (int h = 0; h < 2; ++h) {         // two halves of 16 columns: all loads of a half are in flight before its stores
+    uint4 xb[2];
+    float4 ad[4];
 #pragma unroll
-      for (int e = 0; e < 8; ++e) o[e] = __uint_as_float(v[8 * q + e]) * as;
-      if (xrow != nullptr) {
-        const uint4 xb = *reinterpret_cast<const uint4*>(xrow + c);
-        const uint32_t xw[4] = {xb.x, xb.y, xb.z, xb.w};
+    for (int qq = 0; qq < 2; ++qq) {
+      const int c = col0 + 16 * h + 8 * qq;
+      const bool in = c < pr.N;
+      xb[qq] = (xrow != nullptr && in) ? __ldg(reinterpret_cast<const uint4*>(xrow + c)) : make_uint4(0u, 0u, 0u, 0u);
+      ad[2 * qq] = (arow != nullptr && in) ? *reinterpret_cast<const float4*>(arow + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+      ad[2 * qq + 1] =
+          (arow != nullptr && in) ? *reinterpret_cast<const float4*>(arow + c + 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          float x0, x1;
-          if (pr.fix_f16) {
-            const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&xw[e]));
-            x0 = f.x;
-            x1 = f.y;
-          } else {
-            x0 = __uint_as_float(xw[e] << 16);
-            x1 = __uint_as_float(xw[e] & 0xffff0000u);
+    for (int qq = 0; qq < 2; ++qq) {    // 8 columns at a time (N % 8 == 0 is enforced by the host)
+      const int q = 2 * h + qq;
+      const int c = col0 + 8 * q;
+      if (c < pr.N) {
+        float o[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) o[e] = __uint_as_float(v[8 * q + e]) * as;
+        if (xrow != nullptr) {
+          const uint32_t xw[4] = {xb[qq].x, xb[qq].y, xb[qq].z, xb[qq].w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            float x0, x1;
+            if (pr.fix_f16) {
+              const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&xw[e]));
+              x0 = f.x;
+              x1 = f.y;
+            } else {
+              x0 = __uint_as_float(xw[e] << 16);
+              x1 = __uint_as_float(xw[e] & 0xffff0000u);
+            }
+            o[2 * e + 0] = fmaf(fixs, x0, o[2 * e + 0]);
+            o[2 * e + 1] = fmaf(fixs, x1, o[2 * e + 1]);
           }
-          o[2 * e + 0] = fmaf(fixs, x0, o[2 * e + 0]);
-          o[2 * e + 1] = fmaf(fixs, x1, o[2 * e + 1]);
         }
-      }
-#pragma unroll
-      for (int e = 0; e < 8; ++e) o[e] *= scale;
-      if (arow != nullptr) {
-        const float4 a0 = *reinterpret_cast<const float4*>(arow + c);
-        const float4 a1 = *reinterpret_cast<const float4*>(arow + c + 4);
-        o[0] += a0.x; o[1] += a0.y; o[2] += a0.z; o[3] += a0.w;
-        o[4] += a1.x; o[5] += a1.y; o[6] += a1.z; o[7] += a1.w;
-      }
-      if (pr.out_bf16) {
-        __nv_bfloat16* orow = reinterpret_cast<__nv_bfloat16*>(pr.out) + static_cast<long long>(row) * pr.ldo;
-        *reinterpret_cast<uint4*>(orow + c) =
-            make_uint4(pack_16x2<false>(o[0], o[1]), pack_16x2<false>(o[2], o[3]), pack_16x2<false>(o[4], o[5]),
-                       pack_16x2<false>(o[6], o[7]));
-      } else {
-        float* orow = reinterpret_cast<float*>(pr.out) + static_cast<long long>(row) * pr.ldo;
-        *reinterpret_cast<float4*>(orow + c) = make_float4(o[0], o[1], o[2], o[3]);
-        *reinterpret_cast<float4*>(orow + c + 4) = make_float4(o[4], o[5], o[6], o[7]);
+        const float4 a0 = ad[2 * qq], a1 = ad[2 * qq + 1];   // zeros without a running sum
+        o[0] = fmaf(o[0], scale, a0.x); o[1] = fmaf(o[1], scale, a0.y);
+        o[2] = fmaf(o[2], scale, a0.z); o[3] = fmaf(o[3], scale, a0.w);
+        o[4] = fmaf(o[4], scale, a1.x); o[5] = fmaf(o[5], scale, a1.y);
+        o[6] = fmaf(o[6], scale, a1.z); o[7] = fmaf(o[7], scale, a1.w);
+        if (pr.out_bf16) {
+          __nv_bfloat16* orow = reinterpret_cast<__nv_bfloat16*>(pr.out) + static_cast<long long>(row) * pr.ldo;
+          *reinterpret_cast<uint4*>(orow + c) =
+              make_uint4(pack_16x2<false>(o[0], o[1]), pack_16x2<false>(o[2], o[3]), pack_16x2<false>(o[4], o[5]),
+                         pack_16x2<false>(o[6], o[7]));
+        } else {
+          float* orow = reinterpret_cast<float*>(pr.out) + static_cast<long long>(row) * pr.ldo;
+          *reinterpret_cast<float4*>(orow + c) = make_float4(o[0], o[1], o[2], o[3]);
+          *reinterpret_cast<float4*>(orow + c + 4) = make_float4(o[4], o[5], o[6], o[7]);
+        }
       }
     }
   }
@@ -460,6 +474,7 @@ siglip_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_consta
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  if (p.aux_trace != nullptr && blockIdx.x == 0 && threadIdx.x == 0) p.aux_trace[4] = globaltimer_ns();   // kernel entry
   static_assert(kMC == 1 || kMC == 2, "operand multicast across 1 or 2 tiles");
   // Cluster layout: kCG consecutive CTAs form one MMA pair; kMC pairs (or single CTAs) on vertically adjacent tiles
   // share the B operand tile by TMA multicast. cg=2, mc=2 is the 2x2 cluster cuBLAS' nvjet kernels use.
@@ -505,6 +520,14 @@ siglip_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_consta
   tc_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_ptr_smem));
+  // Programmatic dependent launch: everything above (barriers, TMEM, descriptor prefetch) touched no global memory and
+  // may run while the previous kernel of the stream drains its last tiles; from here on its results are needed (and the
+  // buffers it read are overwritten). The next kernel of the stream may start ITS set-up as soon as SMs free up.
+  if (p.pdl) {
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  }
+  if (p.aux_trace != nullptr && blockIdx.x == 0 && threadIdx.x == 0) p.aux_trace[5] = globaltimer_ns();   // set-up done
 
   if (warp == kProducerWarp) {
     // ===================================== TMA producer =====================================
@@ -633,6 +656,8 @@ siglip_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_consta
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(full_bar(stage), phase, p.dbg, 3, t, kb, 0, prof ? &w_full : nullptr);
           tc_fence_after();
+          if (p.aux_trace != nullptr && blockIdx.x == 0 && lane == 0 && t == cluster_id && kb == kb0)
+            p.aux_trace[6] = globaltimer_ns();                                   // first operands have landed
           const long long c0 = prof ? clock_cycles() : 0;
           long long c1 = 0;
           if (elect_one_sync()) {
@@ -685,6 +710,7 @@ siglip_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_consta
           aphase ^= 1u;
         }
       }
+      if (p.aux_trace != nullptr && blockIdx.x == 0 && lane == 0) p.aux_trace[7] = globaltimer_ns();  // last MMA issued
       if (prof) {
         // the elected lane accumulated issue/commit; every lane has the (identical) wait counters
         const long long wi = __reduce_max_sync(0xffffffffu, static_cast<int>(w_issue >> 8));
@@ -1410,19 +1436,26 @@ int launch_impl(const CUtensorMap* tmA0, const CUtensorMap* tmB0, const CUtensor
   using C = Cfg<kCG, kMode, kStages>;
   constexpr int kClusterSize = kCG * kMC;
   auto kern = siglip_gemm_kernel<kCG, kMode, kStages, kMC>;
-  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes);
-  if (e != cudaSuccess) return static_cast<int>(e);
+  static bool attr_set = false;
+  cudaError_t e = cudaSuccess;
+  if (!attr_set) {
+    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes);
+    if (e != cudaSuccess) return static_cast<int>(e);
+    attr_set = true;
+  }
   int total_tiles = ((p.prob[0].tiles_m + kMC - 1) / kMC) * p.prob[0].tiles_n;
   if (p.nprob > 1) total_tiles += ((p.prob[1].tiles_m + kMC - 1) / kMC) * p.prob[1].tiles_n;
   cudaLaunchConfig_t cfg{};
   cfg.blockDim = dim3(kNumThreads);
   cfg.dynamicSmemBytes = C::kSmemBytes;
   cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = kClusterSize;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   // A persistent kernel must have every cluster co-resident: clusters of 4 do not tile every GPC, so ask the runtime
@@ -1466,6 +1499,7 @@ int launch_impl(const CUtensorMap* tmA0, const CUtensorMap* tmB0, const CUtensor
   if (clusters > total_tiles) clusters = total_tiles;
   if (clusters < 1) clusters = 1;
   cfg.gridDim = dim3(clusters * kClusterSize);
+  cfg.numAttrs = pl.pdl ? 2 : 1;
   e = cudaLaunchKernelEx(&cfg, kern, *tmA0, *tmB0, *tmA1, *tmB1, *tmG, pl);
   return static_cast<int>(e);
 }

@@ -117,6 +117,7 @@ struct KernelParams {
   size_t sk_ws_bytes;
   unsigned int* sk_counters;   // [sk_tiles][2]: arrivals of the non-owner warps, owner warps that consumed them
   int sk_max_tiles;            // capacity of sk_counters
+  int pdl;                     // 1: launched with programmatic stream serialization (griddepcontrol in the kernel)
   unsigned long long peer_timeout_ns;  // bound of every wait on a peer flag (a dead peer traps instead of hanging)
   unsigned long long* aux_trace;       // optional [4] globaltimer stamps of CTA 0's aux thread: start, flags seen, jobs done
 };

@@ -111,13 +111,13 @@ class SigmoidLossEngine:
         _capi.check(self._L.siglip_debug_set_mailbox(self._h, peer, float(dt_prime), float(dbias)))
 
     def aux_trace(self, max_launches: int = 4096):
-        """[(start, flags_seen, jobs_done, launch_end)] globaltimer ns per launch since the last call; needs
-        SIGLIP_OPT_AUX_TRACE."""
-        buf = (ctypes.c_ulonglong * (4 * max_launches))()
+        """Per launch since the last call, globaltimer ns: (aux start, flags seen, aux jobs done, launch end, kernel
+        entry, set-up done, first operands landed, last MMA issued); needs SIGLIP_OPT_AUX_TRACE."""
+        buf = (ctypes.c_ulonglong * (8 * max_launches))()
         n = ctypes.c_int(0)
         _capi.check(self._L.siglip_ctx_aux_trace(self._h, ctypes.cast(buf, ctypes.c_void_p), max_launches,
                                                  ctypes.byref(n)))
-        return [tuple(int(buf[4 * i + j]) for j in range(4)) for i in range(n.value)]
+        return [tuple(int(buf[8 * i + j]) for j in range(8)) for i in range(n.value)]
 
     @property
     def workspace_bytes(self) -> int:

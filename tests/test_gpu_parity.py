@@ -1083,7 +1083,7 @@ def test_peer_timeout_option_and_trace_hook():
     eng.fwd_bwd(img, txt, _scal(1.0), _scal(-5.0))
     tr = eng.aux_trace()
     assert len(tr) == 4                       # L0 L1 G1 G0
-    for (t0, tflag, tdone, tend) in tr:
+    for (t0, tflag, tdone, tend, *_rest) in tr:
         assert t0 > 0 and tdone >= t0 and (tend == 0 or tend >= t0)
     eng.close()
 
@@ -1145,3 +1145,27 @@ def test_fp8_measurement_path_computes_the_e4m3_product(cg, monkeypatch):
         torch.cuda.synchronize()
         ref = A.float() @ Bm.float().T
         assert float((C - ref).abs().max()) <= 1e-5 * float(ref.abs().max()) * math.sqrt(K) + 1e-4
+
+
+def test_programmatic_dependent_launch_changes_nothing_but_timing():
+    """SIGLIP_OPT_PDL: the kernels' set-up may overlap the previous kernel's tail; every global access stays ordered
+    behind it (griddepcontrol.wait), so results are bitwise those of plain launches — also back to back on one stream
+    with a multi-chunk loopback schedule, where consecutive launches hand sigma operands and flags to each other."""
+    from distributed_sigmoid_loss_b200 import _capi
+    B, D, W = 1024, 256, 3
+    img, txt = _synth(B, D, seed=21)
+    tp, b = _scal(math.log(10.0)), _scal(-10.0)
+    outs = {}
+    for pdl in (0, 1):
+        eng = _engine(B, D, 2, rank_world=(1, W), loopback=True)
+        eng.set_option(_capi.SIGLIP_OPT_PDL, pdl)
+        for k in range(W):
+            eng.debug_set_text_chunk(k, _synth(B, D, seed=40 + k)[1])
+        res = None
+        for _ in range(6):          # back-to-back steps: no host synchronisation between the launches
+            res = eng.fwd_bwd(img, txt, tp, b)
+        torch.cuda.synchronize()
+        outs[pdl] = [x.clone() for x in res] + [eng.debug_get_slot(0).clone(), eng.debug_get_slot(2).clone()]
+        eng.close()
+    for x, y in zip(outs[0], outs[1]):
+        assert torch.equal(x, y)

@@ -175,7 +175,7 @@ def main() -> int:
             tr = eng.aux_trace()
             eng.set_option(_capi.SIGLIP_OPT_AUX_TRACE, 0)
             rows = []
-            for (t0, tflag, tdone, tend) in tr[-2 * world:]:          # the last step: L0 L1 G1 ... G0
+            for (t0, tflag, tdone, tend, *_rest) in tr[-2 * world:]:          # the last step: L0 L1 G1 ... G0
                 wait_us = (tflag - t0) / 1e3 if tflag else 0.0
                 jobs_us = (tdone - (tflag if tflag else t0)) / 1e3
                 kern_us = (tend - t0) / 1e3 if tend else float("nan")
