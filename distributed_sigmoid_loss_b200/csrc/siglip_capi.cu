@@ -174,7 +174,8 @@ struct siglip_ctx {
   int saved_f16 = 0;                     // format of the embeddings of the forward saved for backward
   int pdl = 1;                           // programmatic dependent launch of the tcgen05 kernels (set-up overlaps the previous tail)
   int inkernel_sync = 1;                 // fused step: flags waited for / raised inside the tcgen05 kernels (0: helper launches)
-  int split_k = -1;                      // gradient kernel: -1 = choose, 0 = off, S >= 2 = split the tiles of a ragged last wave
+  int split_k = 0;                       // gradient kernel: 0 = off (default: measured no gain, profiles/r02_notes.md), -1 = split a
+                                         // ragged last wave automatically, S >= 2 = at most S slices
   long long peer_timeout_ms = 600000;    // bound of every wait on a peer (10 min: a peer may be saving a checkpoint)
   int aux_trace_on = 0;
   // diagnostics, read from the environment once at context creation (see include/siglip_b200.h)
@@ -196,7 +197,7 @@ struct siglip_ctx {
   float* loop_mailboxes = nullptr;       // loopback only: [world][2] stand-ins for the peers' (dt', dbias) mailboxes
   float* loop_zero = nullptr;            // loopback only: [world][Bmax, D] zeros standing in for the peers' contribution slots
   float* scalars = nullptr;              // [24] device scalars: host API staging, saved dt'/dbias of the last forward
-  unsigned long long* aux_trace = nullptr;  // [kTraceLaunches][8] globaltimer stamps (SIGLIP_OPT_AUX_TRACE)
+  unsigned long long* aux_trace = nullptr;  // [kTraceLaunches][12] globaltimer stamps (SIGLIP_OPT_AUX_TRACE)
   float* splitk_ws = nullptr;            // fp32 partial accumulators of the split tiles of the gradient kernel
   unsigned int* splitk_counters = nullptr;  // per split tile: arrivals of the non-owner parts (monotonic)
   size_t splitk_ws_bytes = 0;
@@ -339,7 +340,7 @@ void apply_aux(siglip_ctx* c, KernelParams& p, const AuxList& aux, const EndSign
     p.end_ticket = c->sync_words + kSyncEndTicket;
   }
   if (c->aux_trace_on && c->aux_trace != nullptr && c->aux_trace_n < kTraceLaunches) {
-    p.aux_trace = c->aux_trace + 8ull * c->aux_trace_n;
+    p.aux_trace = c->aux_trace + 12ull * c->aux_trace_n;
     c->aux_trace_n++;
   }
 }
@@ -498,7 +499,7 @@ int run_grad_chunk(siglip_ctx* c, int gi, bool own, const void* img, const __nv_
       return static_cast<double>((tiles + units - 1) / units) * row_cost / static_cast<double>(cols);
     };
     tile_n = (c->mcast == 1 && cost(128) < 0.97 * cost(256)) ? 128 : 256;
-    if (c->split_k != 0 && c->mcast == 1) tile_n = 256;   // split-K evens out the last wave of full-width tiles instead
+    if (c->split_k != 0 && c->mcast == 1) tile_n = 256;   // split-K (when asked for) evens out the last wave instead
   }
   if (c->mcast != 1) tile_n = 256;
   for (int i = 0; i < 2; ++i) {
@@ -1136,9 +1137,13 @@ int siglip_ctx_set_option(siglip_ctx* c, int option, int value) {
       c->aux_trace_n = 0;
       if (value && c->aux_trace == nullptr) {
         CK(cudaSetDevice(c->device));
-        CK(cudaMalloc(reinterpret_cast<void**>(&c->aux_trace), kTraceLaunches * 8 * sizeof(unsigned long long)));
+        CK(cudaMalloc(reinterpret_cast<void**>(&c->aux_trace), kTraceLaunches * 12 * sizeof(unsigned long long)));
       }
-      if (value) CK(cudaMemset(c->aux_trace, 0, kTraceLaunches * 8 * sizeof(unsigned long long)));
+      if (value) {
+        std::vector<unsigned long long> init(static_cast<size_t>(kTraceLaunches) * 12, 0ull);
+        for (unsigned int i = 0; i < kTraceLaunches; ++i) init[12ull * i + 8] = init[12ull * i + 10] = ~0ull;  // minima
+        CK(cudaMemcpy(c->aux_trace, init.data(), init.size() * sizeof(unsigned long long), cudaMemcpyHostToDevice));
+      }
       return 0;
     default:
       return fail(SIGLIP_ERR_INVALID, "unknown option");
@@ -1494,7 +1499,7 @@ int siglip_ctx_aux_trace(siglip_ctx* c, unsigned long long* out, int max_launche
   CK(cudaDeviceSynchronize());
   int n = static_cast<int>(c->aux_trace_n);
   if (n > max_launches) n = max_launches;
-  if (n > 0) CK(cudaMemcpy(out, c->aux_trace, static_cast<size_t>(n) * 8 * sizeof(unsigned long long),
+  if (n > 0) CK(cudaMemcpy(out, c->aux_trace, static_cast<size_t>(n) * 12 * sizeof(unsigned long long),
                            cudaMemcpyDeviceToHost));
   *n_launches = n;
   c->aux_trace_n = 0;

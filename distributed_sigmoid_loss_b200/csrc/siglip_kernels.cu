@@ -22,6 +22,8 @@
 #include <stdio.h>
 #include <stdlib.h>
 
+#include <type_traits>
+
 namespace siglip {
 
 namespace {
@@ -253,7 +255,7 @@ __device__ __forceinline__ void item_k_range(const KernelParams& p, const TileCo
 // bias ~ -10): 1 MUFU (ex2) + ~6 packed FMA-pipe instructions per element, sigma and log1p by their series.
 // General path: any z, exp(-|z|) + degree-7 log1p polynomial + rcp.
 // -------------------------------------------------------------------------------------------------
-constexpr float kFastZ = -4.2f;  // e < 0.015 < 2^-6: series truncation e^4/5 < 1.1e-8 relative
+constexpr float kFastZ = -4.2f;  // e < 0.015 < 2^-6: series truncated after e^2, relative error < e^3 = 3.4e-6
 
 // The sigma slab goes to HBM through shared memory + one TMA store per warp: 4 conflict-free 16-byte
 // st.shared per thread instead of 4 strided 16-byte global stores (32 cache lines per instruction).
@@ -289,7 +291,8 @@ __device__ __forceinline__ void store_g_slab(const GStore& gs, int col0, const u
 }
 
 // Fast path: every z of the slab is < kFastZ, so e = exp(z) < 2^-6 and both sigma(z) = e / (1 + e) and log1p(e) are
-// evaluated by their alternating series on the FMA pipe (truncation < 6e-8 relative), two elements per instruction
+// evaluated by their alternating series on the FMA pipe (truncation < 3.4e-6 relative at the edge of the path, < 1e-8
+// for the z ~ -10 of a SigLIP batch; the tolerance is 1e-3), two elements per instruction
 // (FFMA2 / FMUL2 / FADD2). One MUFU (ex2) per element instead of two: the epilogue of this kernel is bound by the
 // MUFU and FMA pipes, not by the tensor pipe it has to keep up with.
 template <bool kF16>
@@ -301,7 +304,7 @@ __device__ __forceinline__ void loss_slab_fast(const uint32_t (&v)[32], float tl
   // sigma is produced already multiplied by the power-of-two scale of the 16-bit operand (exact), and the two sums
   // that use it are un-scaled once per slab
   const f32x2 gs_p = pack2(gscale, gscale), gs_n = pack2(-gscale, -gscale), one = pack2(1.0f, 1.0f);
-  const f32x2 c3 = pack2(-0.25f, -0.25f), c2 = pack2(0.33333334f, 0.33333334f), c1 = pack2(-0.5f, -0.5f);
+  const f32x2 c2 = pack2(0.33333334f, 0.33333334f), c1 = pack2(-0.5f, -0.5f);
   f32x2 a_sp = pack2(0.f, 0.f), a_g = pack2(0.f, 0.f), a_gs = pack2(0.f, 0.f);
 #pragma unroll
   for (int j = 0; j < 16; ++j) {
@@ -310,12 +313,16 @@ __device__ __forceinline__ void loss_slab_fast(const uint32_t (&v)[32], float tl
     float t1a, t1b;
     unpack2(t1, t1a, t1b);
     const f32x2 e = pack2(ex2_approx(t1a), ex2_approx(t1b));   // exp(z), z < kFastZ
-    f32x2 q = fma2(e, gs_n, gs_p);                         // S sigma(z) / e = S (1 - e + e^2 - e^3)
+#ifndef SIGLIP_EXP_OLDSERIES
+    f32x2 q = fma2(e, gs_p, gs_n);                         // S sigma(z) / e = S (1 - e + e^2)   [- e^3 < 3.8e-6 dropped]
+    q = fma2(e, q, gs_p);
+#else
+    f32x2 q = fma2(e, gs_n, gs_p);
     q = fma2(e, q, gs_n);
     q = fma2(e, q, gs_p);
+#endif
     const f32x2 g = mul2(e, q);                            // S sigma(z)
-    f32x2 l = fma2(e, c3, c2);                             // log1p(e) / e = 1 - e/2 + e^2/3 - e^3/4
-    l = fma2(e, l, c1);
+    f32x2 l = fma2(e, c2, c1);                             // log1p(e) / e = 1 - e/2 + e^2/3     [- e^3/4 < 1e-6 dropped]
     l = fma2(e, l, one);
     a_sp = fma2(e, l, a_sp);
     a_g = add2(a_g, g);
@@ -338,7 +345,7 @@ __device__ __forceinline__ void loss_slab_fast(const uint32_t (&v)[32], float tl
 template <bool kEdge, bool kDiag, bool kF16>
 __device__ __forceinline__ void loss_slab(const uint32_t (&v)[32], float t, float b, int row, int col0, int nrows,
                                           int ncols, bool store_g, const GStore& gst, float gscale, float* g_diag,
-                                          float& acc_sp, float& acc_g, float& acc_gs) {
+                                          float& acc_sp, float& acc_g, float& acc_gs, bool on_diag = true) {
   uint32_t packed[16];
   float g_prev = 0.f;
 #pragma unroll
@@ -355,7 +362,7 @@ __device__ __forceinline__ void loss_slab(const uint32_t (&v)[32], float t, floa
     bool valid = true;
     if constexpr (kEdge) valid = (row < nrows) && (col0 + j < ncols);
     if constexpr (kDiag) {
-      if (row == col0 + j) {                           // positive pair (label +1): softplus(-z), -sigma(-z)
+      if (on_diag && row == col0 + j) {                // positive pair (label +1): softplus(-z), -sigma(-z)
         sp = fmaxf(-z, 0.f) + l;
         g = -((z >= 0.f) ? e * r : r);                 // sigma(-z) without the 1 - sigma(z) cancellation
         g_store = 0.f;                                 // the 16-bit operand carries negatives only
@@ -523,10 +530,12 @@ siglip_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_consta
   // Programmatic dependent launch: everything above (barriers, TMEM, descriptor prefetch) touched no global memory and
   // may run while the previous kernel of the stream drains its last tiles; from here on its results are needed (and the
   // buffers it read are overwritten). The next kernel of the stream may start ITS set-up as soon as SMs free up.
+#ifndef SIGLIP_EXP_NOGDC
   if (p.pdl) {
     asm volatile("griddepcontrol.wait;" ::: "memory");
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   }
+#endif
   if (p.aux_trace != nullptr && blockIdx.x == 0 && threadIdx.x == 0) p.aux_trace[5] = globaltimer_ns();   // set-up done
 
   if (warp == kProducerWarp) {
@@ -653,64 +662,76 @@ siglip_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_consta
         mbar_wait(tmem_empty_bar(as), aphase ^ 1u, p.dbg, 2, t, as, 0, prof ? &w_tmem : nullptr);
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(as * kTileN);
-        for (int kb = kb0; kb < kb1; ++kb) {
-          mbar_wait(full_bar(stage), phase, p.dbg, 3, t, kb, 0, prof ? &w_full : nullptr);
-          tc_fence_after();
-          if (p.aux_trace != nullptr && blockIdx.x == 0 && lane == 0 && t == cluster_id && kb == kb0)
-            p.aux_trace[6] = globaltimer_ns();                                   // first operands have landed
-          const long long c0 = prof ? clock_cycles() : 0;
-          long long c1 = 0;
-          if (elect_one_sync()) {
-            const uint64_t adesc = adesc0 + static_cast<uint64_t>(stage * (C::kStageBytes >> 4));
-            const uint64_t bdesc = bdesc0 + static_cast<uint64_t>(stage * (C::kStageBytes >> 4));
-            if (!fp8) {
+        if (p.aux_trace != nullptr && blockIdx.x == 0 && t == cluster_id) {     // diagnostic, first tile only
+          mbar_wait(full_bar(stage), phase, p.dbg, 3, t, kb0, 0, nullptr);
+          if (lane == 0) p.aux_trace[6] = globaltimer_ns();                      // first operands have landed
+        }
+        // The k loop is the critical path of the kernel (one elected lane feeds the tensor pipe): keep it free of
+        // anything that is not the four MMAs and the two commits. The 8-bit measurement variant gets its own copy.
+        auto issue_tile = [&](auto is_fp8) {
+          for (int kb = kb0; kb < kb1; ++kb) {
+            mbar_wait(full_bar(stage), phase, p.dbg, 3, t, kb, 0, prof ? &w_full : nullptr);
+            tc_fence_after();
+            const long long c0 = prof ? clock_cycles() : 0;
+            long long c1 = 0;
+            if (elect_one_sync()) {
+              const uint64_t adesc = adesc0 + static_cast<uint64_t>(stage * (C::kStageBytes >> 4));
+              const uint64_t bdesc = bdesc0 + static_cast<uint64_t>(stage * (C::kStageBytes >> 4));
 #pragma unroll
               for (int k = 0; k < kBlockK / kUmmaK; ++k) {
-                umma_bf16<kCG>(tmem_d, adesc + static_cast<uint64_t>(k * a_adv),
+                if constexpr (decltype(is_fp8)::value) {   // kind::f8f6f4: 32 e4m3 values (32 bytes) per instruction
+                  umma_f8<kCG>(tmem_d, adesc + static_cast<uint64_t>(k * a_adv),
                                bdesc + static_cast<uint64_t>(k * b_adv), idesc,
                                static_cast<uint32_t>(kb != kb0 || k != 0));
+                } else {
+                  umma_bf16<kCG>(tmem_d, adesc + static_cast<uint64_t>(k * a_adv),
+                                 bdesc + static_cast<uint64_t>(k * b_adv), idesc,
+                                 static_cast<uint32_t>(kb != kb0 || k != 0));
+                }
               }
-            } else {   // kind::f8f6f4: 32 e4m3 values (32 bytes) per instruction along K — same byte geometry
-#pragma unroll
-              for (int k = 0; k < kBlockK / kUmmaK; ++k) {
-                umma_f8<kCG>(tmem_d, adesc + static_cast<uint64_t>(k * a_adv),
-                             bdesc + static_cast<uint64_t>(k * b_adv), idesc,
-                             static_cast<uint32_t>(kb != kb0 || k != 0));
-              }
-            }
-            c1 = prof ? clock_cycles() : 0;
-            if constexpr (kMC > 1 && kCG == 1) {
-              umma_commit_mcast(empty_bar(stage), kMcMask);  // stage is free in every CTA that writes into it
-            } else if constexpr (kMC > 1) {
-              umma_commit_2sm_mask(empty_bar(stage), kMcMask);   // all four CTAs of the 2x2 cluster
-            } else {
-              umma_commit<kCG>(empty_bar(stage));  // frees the smem stage (both CTAs) when the MMAs retire
-            }
-            if (kb == kb1 - 1) {                   // accumulator ready for the epilogue warps of this pair
-              if constexpr (kMC > 1 && kCG == 2) {
-                umma_commit_2sm_mask(tmem_full_bar(as), static_cast<uint16_t>(0x3u << leader_rank));
+              c1 = prof ? clock_cycles() : 0;
+              if constexpr (kMC > 1 && kCG == 1) {
+                umma_commit_mcast(empty_bar(stage), kMcMask);  // stage is free in every CTA that writes into it
+              } else if constexpr (kMC > 1) {
+                umma_commit_2sm_mask(empty_bar(stage), kMcMask);   // all four CTAs of the 2x2 cluster
               } else {
-                umma_commit<kCG>(tmem_full_bar(as));
+                umma_commit<kCG>(empty_bar(stage));  // frees the smem stage (both CTAs) when the MMAs retire
+              }
+              if (kb == kb1 - 1) {                   // accumulator ready for the epilogue warps of this pair
+                if constexpr (kMC > 1 && kCG == 2) {
+                  umma_commit_2sm_mask(tmem_full_bar(as), static_cast<uint16_t>(0x3u << leader_rank));
+                } else {
+                  umma_commit<kCG>(tmem_full_bar(as));
+                }
+              }
+              if (prof) {
+                const long long c2 = clock_cycles();
+                w_issue += c1 - c0;
+                w_commit += c2 - c1;
               }
             }
-            if (prof) {
-              const long long c2 = clock_cycles();
-              w_issue += c1 - c0;
-              w_commit += c2 - c1;
+            __syncwarp();
+            if (++stage == C::kStages) {
+              stage = 0;
+              phase ^= 1u;
             }
           }
-          __syncwarp();
-          if (++stage == C::kStages) {
-            stage = 0;
-            phase ^= 1u;
-          }
-        }
+        };
+        if (fp8)
+          issue_tile(std::true_type{});
+        else
+          issue_tile(std::false_type{});
         if (++as == kAccStages) {
           as = 0;
           aphase ^= 1u;
         }
       }
-      if (p.aux_trace != nullptr && blockIdx.x == 0 && lane == 0) p.aux_trace[7] = globaltimer_ns();  // last MMA issued
+      if (p.aux_trace != nullptr && lane == 0) {
+        const unsigned long long now = globaltimer_ns();
+        if (blockIdx.x == 0) p.aux_trace[7] = now;                    // last MMA issued (CTA 0)
+        atomicMax(p.aux_trace + 9, now);                              // ... latest / earliest over the issuing CTAs
+        atomicMin(p.aux_trace + 10, now);
+      }
       if (prof) {
         // the elected lane accumulated issue/commit; every lane has the (identical) wait counters
         const long long wi = __reduce_max_sync(0xffffffffu, static_cast<int>(w_issue >> 8));
@@ -831,13 +852,11 @@ siglip_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_consta
               loss_slab_fast<true>(v, tl, bl, col0, sg, gst, p.g_scale, acc_sp, acc_g, acc_gs);
             else
               loss_slab<false, false, true>(v, t_eff, bias, row, col0, pr.M, pr.N, sg, gst, p.g_scale, p.g_diag, acc_sp, acc_g, acc_gs);
-          } else if (edge) {
-            if (diag)
-              loss_slab<true, true, true>(v, t_eff, bias, row, col0, pr.M, pr.N, sg, gst, p.g_scale, p.g_diag, acc_sp, acc_g, acc_gs);
-            else
-              loss_slab<true, false, true>(v, t_eff, bias, row, col0, pr.M, pr.N, sg, gst, p.g_scale, p.g_diag, acc_sp, acc_g, acc_gs);
           } else {
-            loss_slab<false, true, true>(v, t_eff, bias, row, col0, pr.M, pr.N, sg, gst, p.g_scale, p.g_diag, acc_sp, acc_g, acc_gs);
+            // edge and / or diagonal tiles (a few per chunk): ONE masked variant — two more copies of the unrolled
+            // general path only made the kernel's code larger (the loss and gradient kernels alternate and share the
+            // instruction caches)
+            loss_slab<true, true, true>(v, t_eff, bias, row, col0, pr.M, pr.N, sg, gst, p.g_scale, p.g_diag, acc_sp, acc_g, acc_gs, diag);
           }
         } else {
           if (tc.part < 0) {
@@ -961,6 +980,7 @@ siglip_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_consta
         aphase ^= 1u;
       }
     }
+    if (p.aux_trace != nullptr && threadIdx.x == 0) atomicMax(p.aux_trace + 11, globaltimer_ns());   // tiles done
     if (p.wait_stats != nullptr && threadIdx.x == 0) {
       p.wait_stats[8ll * blockIdx.x + 6] = static_cast<unsigned long long>(w_epi);
       p.wait_stats[8ll * blockIdx.x + 7] = static_cast<unsigned long long>(clock_cycles() - epi_start);
@@ -982,13 +1002,25 @@ siglip_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_consta
       named_barrier_sync(1, kNumEpiWarps * 32);
       if (warp == 0) {
         unsigned int ticket = 0;
+#ifndef SIGLIP_EXP_OLDRED
+        // 16 warps x 3 sums: lanes 0..15 take one warp's triple each, fixed shuffle tree (same order every run)
+        double s0 = (lane < kNumEpiWarps) ? red[lane * 3 + 0] : 0.0;
+        double s1 = (lane < kNumEpiWarps) ? red[lane * 3 + 1] : 0.0;
+        double s2 = (lane < kNumEpiWarps) ? red[lane * 3 + 2] : 0.0;
+        s0 = warp_sum(s0);
+        s1 = warp_sum(s1);
+        s2 = warp_sum(s2);
+#else
+        double s0 = 0.0, s1 = 0.0, s2 = 0.0;
         if (lane == 0) {
-          double s0 = 0.0, s1 = 0.0, s2 = 0.0;
           for (int w = 0; w < kNumEpiWarps; ++w) {
             s0 += red[w * 3 + 0];
             s1 += red[w * 3 + 1];
             s2 += red[w * 3 + 2];
           }
+        }
+#endif
+        if (lane == 0) {
           double* slot = p.partials + 4ll * blockIdx.x;
           if (p.accumulate_partials) {
             s0 += slot[0];
@@ -1023,7 +1055,7 @@ siglip_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_consta
               if (p.fin_loss) *p.fin_loss = static_cast<float>(f0 * inv_b);
               if (p.fin_dbias) *p.fin_dbias = static_cast<float>(f1 * inv_b);
               if (p.fin_dt_prime)
-                *p.fin_dt_prime = static_cast<float>(exp(static_cast<double>(*p.t_prime)) * f2 * inv_b);
+                *p.fin_dt_prime = static_cast<float>(static_cast<double>(expf(*p.t_prime)) * f2 * inv_b);
               *p.fin_counter = 0u;                        // ready for the next forward
             }
           }
@@ -1068,12 +1100,9 @@ siglip_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_consta
         // bf16 -> scaled fp16 copies of the embeddings for the gradient kernel (its sigma operand is fp16, and an
         // MMA cannot mix fp16 with bf16): done here, off the critical path, while the tiles of this chunk compute.
         const float sc = p.cvt_scale;
-        for (unsigned long long i = tid0; i < n16; i += nthreads) {
-          const uint4 v = job.src[i];
-          if (job.cvt_copy) {
-            job.dst[i] = v;
-            continue;
-          }
+        const bool plain = job.cvt_copy != 0;
+        auto cvt = [&](uint4 v) {
+          if (plain) return v;
           const uint32_t w[4] = {v.x, v.y, v.z, v.w};
           uint32_t o[4];
 #pragma unroll
@@ -1082,8 +1111,19 @@ siglip_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_consta
             const float hi = fminf(fmaxf(__uint_as_float(w[q] & 0xffff0000u) * sc, -65504.f), 65504.f);
             o[q] = pack_16x2<true>(lo, hi);
           }
-          job.dst[i] = make_uint4(o[0], o[1], o[2], o[3]);
+          return make_uint4(o[0], o[1], o[2], o[3]);
+        };
+        // 8 independent 16-byte loads in flight per thread: with one the loop was latency-bound (0.26 ms for the two
+        // 32 MiB operands of the headline shape, most of the loss kernel's duration, for 128 MiB of traffic)
+        unsigned long long i = tid0;
+        for (; i + 7ull * nthreads < n16; i += 8ull * nthreads) {
+          uint4 v[8];
+#pragma unroll
+          for (int u = 0; u < 8; ++u) v[u] = ld_peer_16(job.src + i + u * nthreads);
+#pragma unroll
+          for (int u = 0; u < 8; ++u) job.dst[i + u * nthreads] = cvt(v[u]);
         }
+        for (; i < n16; i += nthreads) job.dst[i] = cvt(ld_peer_16(job.src + i));
       } else if (job.kind == kAuxFold) {
         const bool has_in = job.src2 != nullptr;   // first contribution of a backward pass: plain copy
         const float4* acc_in = reinterpret_cast<const float4*>(job.src2);
@@ -1140,6 +1180,7 @@ siglip_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_consta
     tmem_dealloc<kCG>(tmem_base, kTmemCols);
   }
   // every warp of this CTA is past its last global write (barrier above): the last CTA of the launch tells the peers
+  if (threadIdx.x == 0 && p.aux_trace != nullptr) atomicMin(p.aux_trace + 8, globaltimer_ns());   // first CTA to finish
   if (threadIdx.x == 0 && p.end_ticket != nullptr) {
     if (last_cta_arrives(p.end_ticket)) {
       for (int i = 0; i < p.end_sig_n; ++i) release_store_sys(p.end_sig_ptrs[i], p.end_sig_value);

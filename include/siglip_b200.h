@@ -76,9 +76,11 @@ enum {
   SIGLIP_OPT_INKERNEL_SYNC = 16, /* 1 (default): siglip_fwd_bwd waits for / raises every cross-rank flag inside its tcgen05
                                     kernels (a W-rank step is exactly 2W launches); 0: separate one-block wait / signal
                                     kernels and a copy around them (A/B measurements) */
-  SIGLIP_OPT_SPLIT_K = 17, /* gradient kernel, tiles of a ragged last wave: -1 (default) choose, 0 never split, S = 2..8
-                              split each of them S ways along K (fp32 partials through a workspace, fixed-order sum:
-                              bitwise independent of which CTA finishes first) */
+  SIGLIP_OPT_SPLIT_K = 17, /* gradient kernel, tiles of a ragged last wave: 0 (default) never split; -1 split them
+                              floor(units / tiles) ways (at most 4) along K; S = 2..8 at most S ways (fp32 partials
+                              through a workspace, fixed-order sum: bitwise independent of which CTA finishes first).
+                              Measured: no gain at the shapes tried (the last wave is not what a short launch waits for),
+                              so it stays opt-in */
   SIGLIP_OPT_PDL = 19, /* 1 (default): the tcgen05 kernels are launched with programmatic stream serialization: their
                           set-up (barriers, TMEM allocation, descriptor prefetch) overlaps the tail of the previous kernel
                           of the stream; griddepcontrol.wait orders every global access behind it. 0: plain launches */
@@ -256,10 +258,11 @@ int siglip_debug_get_slot(siglip_ctx* ctx, int chunk, float* out_dev, void* cuda
 /* Loopback only: seed the (dt_prime, dbias) mailbox standing in for peer rank `peer`, so that the mean computed under
  * SIGLIP_OPT_SYNC_SCALAR_GRADS can be checked against numbers the kernel did not produce itself. */
 int siglip_debug_set_mailbox(siglip_ctx* ctx, int peer, float dt_prime, float dbias);
-/* With SIGLIP_OPT_AUX_TRACE: device-synchronise and copy out 8 globaltimer stamps (ns) per launch since the last call:
+/* With SIGLIP_OPT_AUX_TRACE: device-synchronise and copy out 12 globaltimer stamps (ns) per launch since the last call:
  * [0..2] auxiliary warps of CTA 0: start, last peer flag observed (0 = no wait), jobs done; [3] launch end as seen by
  * the last CTA; [4] kernel entry (CTA 0); [5] set-up done (barriers, TMEM); [6] first operands landed (MMA warp of CTA 0);
- * [7] last MMA issued (CTA 0). `out` holds 8 * max_launches values. */
+ * [7] last MMA issued (CTA 0); [8] first CTA finished; [9] / [10] latest / earliest "last MMA issued" over the CTAs;
+ * [11] last CTA through the epilogue of its tiles. `out` holds 12 * max_launches values. */
 int siglip_ctx_aux_trace(siglip_ctx* ctx, unsigned long long* out, int max_launches, int* n_launches);
 
 void siglip_ctx_destroy(siglip_ctx* ctx);
