@@ -313,14 +313,8 @@ __device__ __forceinline__ void loss_slab_fast(const uint32_t (&v)[32], float tl
     float t1a, t1b;
     unpack2(t1, t1a, t1b);
     const f32x2 e = pack2(ex2_approx(t1a), ex2_approx(t1b));   // exp(z), z < kFastZ
-#ifndef SIGLIP_EXP_OLDSERIES
     f32x2 q = fma2(e, gs_p, gs_n);                         // S sigma(z) / e = S (1 - e + e^2)   [- e^3 < 3.8e-6 dropped]
     q = fma2(e, q, gs_p);
-#else
-    f32x2 q = fma2(e, gs_n, gs_p);
-    q = fma2(e, q, gs_n);
-    q = fma2(e, q, gs_p);
-#endif
     const f32x2 g = mul2(e, q);                            // S sigma(z)
     f32x2 l = fma2(e, c2, c1);                             // log1p(e) / e = 1 - e/2 + e^2/3     [- e^3/4 < 1e-6 dropped]
     l = fma2(e, l, one);
@@ -530,12 +524,10 @@ siglip_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_consta
   // Programmatic dependent launch: everything above (barriers, TMEM, descriptor prefetch) touched no global memory and
   // may run while the previous kernel of the stream drains its last tiles; from here on its results are needed (and the
   // buffers it read are overwritten). The next kernel of the stream may start ITS set-up as soon as SMs free up.
-#ifndef SIGLIP_EXP_NOGDC
   if (p.pdl) {
     asm volatile("griddepcontrol.wait;" ::: "memory");
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   }
-#endif
   if (p.aux_trace != nullptr && blockIdx.x == 0 && threadIdx.x == 0) p.aux_trace[5] = globaltimer_ns();   // set-up done
 
   if (warp == kProducerWarp) {
@@ -1002,7 +994,6 @@ siglip_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_consta
       named_barrier_sync(1, kNumEpiWarps * 32);
       if (warp == 0) {
         unsigned int ticket = 0;
-#ifndef SIGLIP_EXP_OLDRED
         // 16 warps x 3 sums: lanes 0..15 take one warp's triple each, fixed shuffle tree (same order every run)
         double s0 = (lane < kNumEpiWarps) ? red[lane * 3 + 0] : 0.0;
         double s1 = (lane < kNumEpiWarps) ? red[lane * 3 + 1] : 0.0;
@@ -1010,16 +1001,6 @@ siglip_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_consta
         s0 = warp_sum(s0);
         s1 = warp_sum(s1);
         s2 = warp_sum(s2);
-#else
-        double s0 = 0.0, s1 = 0.0, s2 = 0.0;
-        if (lane == 0) {
-          for (int w = 0; w < kNumEpiWarps; ++w) {
-            s0 += red[w * 3 + 0];
-            s1 += red[w * 3 + 1];
-            s2 += red[w * 3 + 2];
-          }
-        }
-#endif
         if (lane == 0) {
           double* slot = p.partials + 4ll * blockIdx.x;
           if (p.accumulate_partials) {

@@ -4,6 +4,8 @@ import ctypes
 import math
 import os
 import re
+import subprocess
+import sys
 
 import pytest
 import torch
@@ -109,3 +111,81 @@ def test_chunk_schedule_covers_every_pair_once(world, bidir):
         assert sorted(chunk_schedule(r, world, bidir)[k] for r in range(world)) == list(range(world))
     if bidir and world >= 3:
         assert chunk_schedule(0, world, True)[1:3] == [1, world - 1]
+
+
+def test_reference_copy_for_the_cpu_arm_is_byte_identical():
+    """tools/fetch_ref.py places the unmodified reference under the git-ignored baseline/_ref; where /root/reference is
+    present (build container) every copied file must have the upstream bytes, and the manifest must say so."""
+    import hashlib
+    import json
+
+    src = "/root/reference"
+    dst = os.path.join(ROOT, "baseline", "_ref")
+    if not os.path.isdir(src):
+        pytest.skip("the reference tree is only present in the build container")
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    try:
+        import fetch_ref
+        assert fetch_ref.fetch(src, quiet=True)
+    finally:
+        sys.path.pop(0)
+    manifest = json.load(open(os.path.join(dst, "MANIFEST.json")))["sha256"]
+    assert "distributed_sigmoid_loss.py" in manifest and "rwightman_sigmoid_loss.py" in manifest
+    for name, digest in manifest.items():
+        a = open(os.path.join(src, name), "rb").read()
+        b = open(os.path.join(dst, name), "rb").read()
+        assert a == b and hashlib.sha256(b).hexdigest() == digest, name
+    # the directory stays out of the history
+    out = subprocess.run(["git", "check-ignore", "baseline/_ref/distributed_sigmoid_loss.py"], cwd=ROOT,
+                         capture_output=True, text=True)
+    assert out.returncode == 0
+
+
+def test_bench_parity_reference_agrees_with_the_pinned_oracle():
+    """bench.py's parity block carries its own fp32 torch restatement of distributed_sigmoid_loss.py:22-47 (the bench
+    may use oracle/ only for its CPU arm): it must agree with the oracle that is pinned on the reference's fixtures."""
+    import importlib.util
+
+    import numpy as np
+    import torch
+
+    from oracle.siglip_oracle import closed_form
+
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(ROOT, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    W, B, D = 3, 24, 40
+    g = torch.Generator().manual_seed(3)
+    img_all = torch.nn.functional.normalize(torch.randn(W * B, D, generator=g))
+    txt_all = torch.nn.functional.normalize(torch.randn(W * B, D, generator=g))
+    tp, bias = math.log(12.0), -7.5
+    ref = closed_form(img_all.numpy(), txt_all.numpy(), tp, bias, W)
+    contrib = [None] * W
+    for r in range(W):
+        loss, dimg, cs, dtp, db = bench._fp32_autograd(img_all[r * B:(r + 1) * B],
+                                                       [txt_all[c * B:(c + 1) * B] for c in range(W)], tp, bias, r)
+        assert abs(loss - ref[r]["loss"]) <= 1e-5 * abs(ref[r]["loss"])
+        assert abs(dtp - ref[r]["dt_prime"]) <= 1e-4 * abs(ref[r]["dt_prime"])
+        assert abs(db - ref[r]["dbias"]) <= 1e-4 * abs(ref[r]["dbias"])
+        assert np.allclose(dimg.numpy(), ref[r]["dimg"], rtol=1e-4, atol=1e-7)
+        contrib[r] = cs
+    for c in range(W):       # text gradient = sum over the ranks' contributions (the all_reduce in bench.py)
+        total = sum(contrib[r][c] for r in range(W))
+        assert np.allclose(total.numpy(), ref[c]["dtxt"], rtol=1e-4, atol=1e-7)
+
+
+def test_module_pads_odd_widths_and_copies_views_without_a_gpu():
+    import torch
+
+    from distributed_sigmoid_loss_b200.loss import _aligned, _pad_dim
+
+    x = torch.randn(6, 5, requires_grad=True)
+    y = _pad_dim(x)
+    assert y.shape == (6, 8) and torch.equal(y[:, :5], x) and float(y[:, 5:].abs().sum()) == 0.0
+    y.sum().backward()
+    assert x.grad.shape == (6, 5)                       # the gradient comes back sliced
+    assert _pad_dim(torch.zeros(3, 16)).shape == (3, 16)
+    base = torch.zeros(4, 19, dtype=torch.bfloat16)
+    v = base[:, 3:11]
+    a = _aligned(v)
+    assert a.is_contiguous() and a.data_ptr() % 16 == 0 and torch.equal(a, v)
