@@ -78,6 +78,7 @@ SIGLIP_OPT_INKERNEL_SYNC = 16
 SIGLIP_OPT_SPLIT_K = 17
 SIGLIP_OPT_AUX_TRACE = 18
 SIGLIP_OPT_PDL = 19
+SIGLIP_OPT_TPRIME_F64 = 20
 
 _lib: Optional[ctypes.CDLL] = None
 

@@ -172,6 +172,7 @@ struct siglip_ctx {
   int grad_tile_n = 0;                   // column-tile width of the gradient kernel: 0 = choose, 128, 256
   int input_f16 = 0;                     // img / txt are fp16(x * kXScale) instead of bf16 (fp32-input path)
   int saved_f16 = 0;                     // format of the embeddings of the forward saved for backward
+  int tprime_f64 = 0;                    // t_prime / dt_prime pointers of forward / backward / fwd_bwd are fp64 device scalars
   int pdl = 1;                           // programmatic dependent launch of the tcgen05 kernels (set-up overlaps the previous tail)
   int inkernel_sync = 1;                 // fused step: flags waited for / raised inside the tcgen05 kernels (0: helper launches)
   int split_k = 0;                       // gradient kernel: 0 = off (default: measured no gain, profiles/r02_notes.md), -1 = split a
@@ -331,6 +332,7 @@ void apply_aux(siglip_ctx* c, KernelParams& p, const AuxList& aux, const EndSign
     if (p.aux[i].sig_n > 0 || p.aux[i].done_flag != nullptr) p.aux[i].ticket = c->sync_words + i;
   }
   p.cvt_scale = kXScale;
+  p.tprime_f64 = c->tprime_f64;
   p.pdl = c->pdl;
   p.peer_timeout_ns = peer_timeout_ns(c);
   if (end.n > 0 || c->aux_trace_on) {
@@ -769,7 +771,7 @@ int backward_impl(siglip_ctx* c, const void* img, const void* txt, const float* 
     CKI(siglip::launch_allreduce_scalars(c->scalars + kSavedScalars, grad_out,
                                          reinterpret_cast<float*>(c->flags + kMailboxOffset), c->mailbox_ptrs_dev,
                                          c->signal_ptrs_dev + 4 * W, c->flags + 4 * kMaxWorld, W, n, dt_prime, dbias,
-                                         peer_timeout_ns(c), c->dbg_dev, st));
+                                         c->tprime_f64, peer_timeout_ns(c), c->dbg_dev, st));
     c->launches++;
   }
   CK(cudaGetLastError());
@@ -932,7 +934,7 @@ int fused_impl(siglip_ctx* c, const void* img, const void* txt, const float* t_p
     CKI(siglip::launch_allreduce_scalars(c->scalars + kSavedScalars, grad_out,
                                          reinterpret_cast<float*>(c->flags + kMailboxOffset), c->mailbox_ptrs_dev,
                                          c->signal_ptrs_dev + 4 * W, c->flags + 4 * kMaxWorld, W, n, dt_prime, dbias,
-                                         peer_timeout_ns(c), c->dbg_dev, st));
+                                         c->tprime_f64, peer_timeout_ns(c), c->dbg_dev, st));
     c->launches++;
   }
   CK(cudaGetLastError());
@@ -1128,6 +1130,9 @@ int siglip_ctx_set_option(siglip_ctx* c, int option, int value) {
     case SIGLIP_OPT_SPLIT_K:
       if (value < -1 || value == 1 || value > 8) return fail(SIGLIP_ERR_INVALID, "split_k must be -1 (auto), 0 (off) or 2..8");
       c->split_k = value;
+      return 0;
+    case SIGLIP_OPT_TPRIME_F64:
+      c->tprime_f64 = value ? 1 : 0;
       return 0;
     case SIGLIP_OPT_PDL:
       c->pdl = value ? 1 : 0;
@@ -1340,14 +1345,16 @@ int siglip_host_submit_grads(siglip_ctx* c, const void* img_host, const void* tx
   CK(cudaMemcpyAsync(c->h_txt[s], txt_host, chunk_bytes, cudaMemcpyHostToDevice, c->copy_stream));
   CK(cudaEventRecord(c->ev_h2d[s], c->copy_stream));
   CK(cudaStreamWaitEvent(st, c->ev_h2d[s], 0));
-  const int saved_bf16 = c->grad_bf16, saved_fmt = c->input_f16;
+  const int saved_bf16 = c->grad_bf16, saved_fmt = c->input_f16, saved_tp64 = c->tprime_f64;
   c->grad_bf16 = with_grads ? 1 : 0;  // gradients that travel back are bf16 (what autograd returns for bf16 inputs)
   c->input_f16 = 0;                   // ... from bf16 host buffers
+  c->tprime_f64 = 0;                  // the staged scalars are fp32
   void* gi = with_grads ? static_cast<void*>(c->h_gimg[s]) : static_cast<void*>(c->h_dimg);
   void* gt = with_grads ? static_cast<void*>(c->h_gtxt[s]) : static_cast<void*>(c->h_dtxt);
   rc = siglip_fwd_bwd(c, c->h_img[s], c->h_txt[s], sc + 0, sc + 1, sc + 2, gi, gt, sc + 3, sc + 4, st);
   c->grad_bf16 = saved_bf16;
   c->input_f16 = saved_fmt;
+  c->tprime_f64 = saved_tp64;
   if (rc) return rc;
   CK(cudaEventRecord(c->ev_step[s], st));
   CK(cudaStreamWaitEvent(c->d2h_stream, c->ev_step[s], 0));

@@ -169,6 +169,11 @@ __device__ __forceinline__ uint4 ld_peer_16(const uint4* p) {
   return v;
 }
 
+// t' as the module holds it: fp64 like the reference's parameter (distributed_sigmoid_loss.py:11), or fp32
+__device__ __forceinline__ float load_t_prime(const KernelParams& p) {
+  return p.tprime_f64 ? static_cast<float>(*reinterpret_cast<const double*>(p.t_prime)) : *p.t_prime;
+}
+
 struct TileCoord {
   int prob;
   int m_blk;
@@ -742,7 +747,7 @@ siglip_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_consta
     const int q = warp & 3;        // TMEM lane quarter this warp may touch
     const int cgrp = warp >> 2;    // which kEpiCols columns of the 256-column accumulator
     const int row_in_cta = q * 32 + lane;
-    const float t_exact = expf(*p.t_prime);
+    const float t_exact = expf(load_t_prime(p));
     const float bias = (kMode == kModeLoss) ? *p.bias : 0.f;
     // loss kernel: z = t_eff * acc + b with t_eff = t * s_scale (the accumulator is 2^8 <img, txt> for fp16 x 16 operands)
     const float s_scale = (kMode == kModeLoss && p.s_scale != 0.f) ? p.s_scale : 1.0f;
@@ -756,7 +761,12 @@ siglip_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_consta
       // backward of the two scalars: saved (upstream gradient 1) * grad_out, by one thread of the launch
       if (blockIdx.x == 0 && threadIdx.x == 0 && p.sc_saved != nullptr) {
         const float g = (p.grad_out != nullptr) ? *p.grad_out : 1.0f;
-        if (p.sc_dt_prime) *p.sc_dt_prime = p.sc_saved[0] * g;
+        if (p.sc_dt_prime) {
+          if (p.tprime_f64)
+            *reinterpret_cast<double*>(p.sc_dt_prime) = static_cast<double>(p.sc_saved[0] * g);
+          else
+            *p.sc_dt_prime = p.sc_saved[0] * g;
+        }
         if (p.sc_dbias) *p.sc_dbias = p.sc_saved[1] * g;
       }
     }
@@ -1036,7 +1046,7 @@ siglip_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_consta
               if (p.fin_loss) *p.fin_loss = static_cast<float>(f0 * inv_b);
               if (p.fin_dbias) *p.fin_dbias = static_cast<float>(f1 * inv_b);
               if (p.fin_dt_prime)
-                *p.fin_dt_prime = static_cast<float>(static_cast<double>(expf(*p.t_prime)) * f2 * inv_b);
+                *p.fin_dt_prime = static_cast<float>(static_cast<double>(expf(load_t_prime(p))) * f2 * inv_b);
               *p.fin_counter = 0u;                        // ready for the next forward
             }
           }
@@ -1274,7 +1284,7 @@ __global__ void allreduce_scalars_kernel(const float* __restrict__ saved, const 
                                          float* mailbox_local, const float* const* __restrict__ mailboxes,
                                          unsigned int* const* __restrict__ signal_ptrs,
                                          const volatile unsigned int* flags_local, int world, unsigned int value,
-                                         float* dt_prime, float* dbias, unsigned long long timeout_ns,
+                                         float* dt_prime, float* dbias, int dtp_f64, unsigned long long timeout_ns,
                                          DebugRecord* dbg) {
   __shared__ float sh[2][32];
   const int i = threadIdx.x;
@@ -1322,7 +1332,12 @@ __global__ void allreduce_scalars_kernel(const float* __restrict__ saved, const 
       b += sh[1][p];
     }
     const float inv_w = 1.0f / static_cast<float>(world);
-    if (dt_prime) *dt_prime = a * inv_w;
+    if (dt_prime) {
+      if (dtp_f64)
+        *reinterpret_cast<double*>(dt_prime) = static_cast<double>(a * inv_w);
+      else
+        *dt_prime = a * inv_w;
+    }
     if (dbias) *dbias = b * inv_w;
   }
 }
@@ -1667,10 +1682,10 @@ int launch_scale(const void* src, void* dst, int is_bf16, const float* g, size_t
 
 int launch_allreduce_scalars(const float* saved, const float* g, float* mailbox_local, const float* const* mailboxes_dev,
                              unsigned int* const* signal_ptrs_dev, const volatile unsigned int* flags_local, int world,
-                             unsigned int value, float* dt_prime, float* dbias, unsigned long long timeout_ns,
-                             DebugRecord* dbg, cudaStream_t stream) {
+                             unsigned int value, float* dt_prime, float* dbias, int dtp_f64,
+                             unsigned long long timeout_ns, DebugRecord* dbg, cudaStream_t stream) {
   allreduce_scalars_kernel<<<1, 32, 0, stream>>>(saved, g, mailbox_local, mailboxes_dev, signal_ptrs_dev, flags_local,
-                                                 world, value, dt_prime, dbias, timeout_ns, dbg);
+                                                 world, value, dt_prime, dbias, dtp_f64, timeout_ns, dbg);
   return static_cast<int>(cudaGetLastError());
 }
 

@@ -64,7 +64,8 @@ struct KernelParams {
   Problem prob[2];
   int nprob;
   // learnable scalars, device memory (reference: distributed_sigmoid_loss.py:11-12)
-  const float* t_prime;
+  const float* t_prime;   // fp32, or fp64 when tprime_f64 (then sc_dt_prime is written as fp64 too)
+  int tprime_f64;
   const float* bias;
   float s_scale;  // loss kernel: accumulator -> <img, txt> (2^-8 when both operands are fp16 x 16; 0 = 1)
   float inv_b;  // 1 / per-rank batch (reference divides by the LOCAL batch, distributed_sigmoid_loss.py:47)
@@ -159,8 +160,8 @@ int launch_scale(const void* src, void* dst, int is_bf16, const float* g, size_t
 // cross-rank flag helpers (peer-mapped pointers)
 int launch_allreduce_scalars(const float* saved, const float* g, float* mailbox_local, const float* const* mailboxes_dev,
                              unsigned int* const* signal_ptrs_dev, const volatile unsigned int* flags_local, int world,
-                             unsigned int value, float* dt_prime, float* dbias, unsigned long long timeout_ns,
-                             DebugRecord* dbg, cudaStream_t stream);
+                             unsigned int value, float* dt_prime, float* dbias, int dtp_f64,
+                             unsigned long long timeout_ns, DebugRecord* dbg, cudaStream_t stream);
 int launch_signal_flags(unsigned int* const* flag_ptrs_dev, int n, unsigned int value, cudaStream_t stream);
 int launch_wait_flags(const volatile unsigned int* flags, int n, unsigned int value, unsigned long long timeout_ns,
                       DebugRecord* dbg, cudaStream_t stream);

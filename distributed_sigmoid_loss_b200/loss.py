@@ -143,6 +143,8 @@ class SigmoidLossEngine:
         opts = dict(device=self.device, dtype=torch.float32)
         scal = torch.empty(3, **opts)                 # loss, dt', dbias in one allocation
         loss, dtp, db = scal[0:1], scal[1:2], scal[2:3]
+        if self._set_tprime_f64(t_prime):
+            dtp = torch.empty(1, device=self.device, dtype=torch.float64)
         dimg = torch.empty(self.batch, self.dim, device=self.device, dtype=grad_dtype)
         dtxt = torch.empty(self.batch, self.dim, device=self.device, dtype=grad_dtype)
         with torch.cuda.device(self.device):
@@ -161,6 +163,7 @@ class SigmoidLossEngine:
                 save_for_backward: bool) -> torch.Tensor:
         """The W loss kernels. Returns loss[1] (fp32). With save_for_backward the context keeps the sigma operands."""
         self._check(img, txt)
+        self._set_tprime_f64(t_prime)
         loss = torch.empty(1, device=self.device, dtype=torch.float32)
         with torch.cuda.device(self.device):
             _capi.check(self._L.siglip_forward(self._h, img.data_ptr(), txt.data_ptr(), t_prime.data_ptr(),
@@ -176,14 +179,17 @@ class SigmoidLossEngine:
         self._check(img, txt)
         self._set_grad_dtype(grad_dtype)
         scal = torch.empty(2, device=self.device, dtype=torch.float32)
+        dtp, db = scal[0:1], scal[1:2]
+        if self._set_tprime_f64(t_prime):
+            dtp = torch.empty(1, device=self.device, dtype=torch.float64)
         dimg = torch.empty(self.batch, self.dim, device=self.device, dtype=grad_dtype)
         dtxt = torch.empty(self.batch, self.dim, device=self.device, dtype=grad_dtype)
         with torch.cuda.device(self.device):
             _capi.check(self._L.siglip_backward(self._h, img.data_ptr(), txt.data_ptr(), t_prime.data_ptr(),
                                                 grad_out.data_ptr() if grad_out is not None else None,
-                                                dimg.data_ptr(), dtxt.data_ptr(), scal[0:1].data_ptr(),
-                                                scal[1:2].data_ptr(), self._stream()))
-        return dimg, dtxt, scal[0:1], scal[1:2]
+                                                dimg.data_ptr(), dtxt.data_ptr(), dtp.data_ptr(), db.data_ptr(),
+                                                self._stream()))
+        return dimg, dtxt, dtp, db
 
     def _set_grad_dtype(self, grad_dtype: torch.dtype) -> None:
         if grad_dtype not in (torch.float32, torch.bfloat16):
@@ -231,6 +237,7 @@ class SigmoidLossEngine:
 
     def fwd(self, img: torch.Tensor, txt: torch.Tensor, t_prime: torch.Tensor, bias: torch.Tensor) -> torch.Tensor:
         self._check(img, txt)
+        self._set_tprime_f64(t_prime)
         loss = torch.empty(1, device=self.device, dtype=torch.float32)
         with torch.cuda.device(self.device):
             _capi.check(self._L.siglip_fwd(self._h, img.data_ptr(), txt.data_ptr(), t_prime.data_ptr(),
@@ -297,6 +304,17 @@ class SigmoidLossEngine:
         if img.dtype != txt.dtype:
             raise RuntimeError("image and text operands must use the same 16-bit format")
         self._set_input_f16(img.dtype == torch.float16)
+
+    def _set_tprime_f64(self, t_prime: torch.Tensor) -> bool:
+        """t' may be handed over as the reference holds it (fp64, distributed_sigmoid_loss.py:11) or as fp32; dt' then
+        comes back in the same dtype. The context option follows the tensor."""
+        if t_prime.dtype not in (torch.float32, torch.float64) or t_prime.numel() != 1 or t_prime.device != self.device:
+            raise RuntimeError("t_prime must be a 1-element fp32 or fp64 tensor on the engine's device")
+        f64 = t_prime.dtype == torch.float64
+        if f64 != getattr(self, "_tprime_f64", False):
+            _capi.check(self._L.siglip_ctx_set_option(self._h, _capi.SIGLIP_OPT_TPRIME_F64, int(f64)))
+            self._tprime_f64 = f64
+        return f64
 
     def _set_input_f16(self, f16: bool) -> None:
         if f16 != getattr(self, "_input_f16", False):
@@ -370,8 +388,16 @@ class _SigmoidLossFn(torch.autograd.Function):
         else:
             img_b = _aligned(img.detach())
             txt_b = _aligned(txt.detach())
-        tp = t_prime.detach().to(device=img.device, dtype=torch.float32).reshape(1)
-        b = bias.detach().to(device=img.device, dtype=torch.float32).reshape(1)
+        # the two scalars go to the kernels as the module holds them (t' fp64 like the reference's parameter, bias
+        # fp32): no conversion kernels in the stream; anything else is converted to fp32 first
+        tp = t_prime.detach()
+        if not (tp.device == img.device and tp.dtype in (torch.float32, torch.float64)):
+            tp = tp.to(device=img.device, dtype=torch.float32)
+        tp = tp.reshape(1)
+        b = bias.detach()
+        if not (b.device == img.device and b.dtype == torch.float32):
+            b = b.to(device=img.device, dtype=torch.float32)
+        b = b.reshape(1)
         ctx.fused = bool(fused and need_grad)
         if ctx.fused:
             # gradients in the dtype autograd would return for these inputs (fp32 when a projection follows)
@@ -413,7 +439,7 @@ class _SigmoidLossFn(torch.autograd.Function):
             else:
                 gi = eng.scale(dimg, g).to(idt) if ctx.needs_input_grad[0] else None
                 gt = eng.scale(dtxt, g).to(tdt) if ctx.needs_input_grad[1] else None
-            sc = eng.scale(torch.cat([dtp, db]), g)
+            sc = eng.scale(torch.cat([dtp.float(), db]), g)
             dtp, db = sc[0:1], sc[1:2]
         else:
             img_b, txt_b, tp, b = saved[:4]

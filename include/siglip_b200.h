@@ -84,6 +84,10 @@ enum {
   SIGLIP_OPT_PDL = 19, /* 1 (default): the tcgen05 kernels are launched with programmatic stream serialization: their
                           set-up (barriers, TMEM allocation, descriptor prefetch) overlaps the tail of the previous kernel
                           of the stream; griddepcontrol.wait orders every global access behind it. 0: plain launches */
+  SIGLIP_OPT_TPRIME_F64 = 20, /* 1: the t_prime pointer given to siglip_forward / siglip_backward / siglip_fwd_bwd(_scaled)
+                                 is an fp64 device scalar — the dtype of the reference's parameter
+                                 (torch.tensor(np.log(10)), distributed_sigmoid_loss.py:11) — and dt_prime is written as
+                                 fp64: the module hands its parameter over without a conversion kernel. Default 0 (fp32) */
   SIGLIP_OPT_AUX_TRACE = 18 /* 1: record globaltimer stamps of the auxiliary warps of CTA 0 for every launch (start,
                                last peer flag seen, jobs done, end of launch); read with siglip_ctx_aux_trace */
 };

@@ -9,6 +9,10 @@ if ROOT not in sys.path:
 
 GOLDEN_DIR = os.path.join(ROOT, "tests", "golden")
 
+# A protocol bug in a (loopback) multi-chunk test must fail the test within seconds, not after the production default of
+# ten minutes: every context created during the test session bounds its waits on "peers" at 30 s.
+os.environ.setdefault("SIGLIP_PEER_TIMEOUT_MS", "30000")
+
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a real B200 (sm_100a) device; run with -m gpu on the GPU box")

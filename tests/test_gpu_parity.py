@@ -1169,3 +1169,26 @@ def test_programmatic_dependent_launch_changes_nothing_but_timing():
         eng.close()
     for x, y in zip(outs[0], outs[1]):
         assert torch.equal(x, y)
+
+
+def test_t_prime_is_taken_in_the_references_own_dtype():
+    """The reference's t_prime is a float64 parameter (torch.tensor(np.log(10)), distributed_sigmoid_loss.py:11): the C ABI
+    reads it (and writes dt_prime) as fp64 under SIGLIP_OPT_TPRIME_F64, which the engine sets from the tensor's dtype —
+    no conversion kernels around the step. Same numbers as the fp32 hand-over (exp is evaluated in fp32 either way)."""
+    B, D = 768, 128
+    img, txt = _synth(B, D, seed=17)
+    eng = _engine(B, D, 2)
+    tp32, b = _scal(math.log(10.0)), _scal(-10.0)
+    tp64 = torch.tensor([math.log(10.0)], device=_dev(), dtype=torch.float64)
+    r32 = eng.fwd_bwd(img, txt, tp32, b)
+    r64 = eng.fwd_bwd(img, txt, tp64, b)
+    l64 = eng.forward(img, txt, tp64, b, True)
+    d64 = eng.backward(img, txt, tp64, _scal(2.0))
+    r32b = eng.fwd_bwd(img, txt, tp32, b)             # and back
+    torch.cuda.synchronize()
+    assert r64[3].dtype == torch.float64 and d64[2].dtype == torch.float64 and r32[3].dtype == torch.float32
+    assert torch.equal(r32[0], r64[0]) and torch.equal(r32[1], r64[1]) and torch.equal(r32[2], r64[2])
+    assert float(r64[3]) == float(r32[3]) and torch.equal(r32[4], r64[4]) and torch.equal(l64, r32[0])
+    assert abs(float(d64[2]) - 2.0 * float(r32[3])) <= 1e-6 * abs(float(r32[3]))
+    assert torch.equal(r32b[1], r32[1]) and torch.equal(r32b[3], r32[3])
+    eng.close()
