@@ -1,5 +1,10 @@
 #!/usr/bin/env python
-"""Interleaved A/B of the round-1 library (tools/_r1_libsiglip_b200.so, built from git b304770) against the current one
+"""Interleaved A/B of the round-1 library against the current one. Build the old library first (it is not kept in the
+tree):   for f in ptx.cuh siglip_kernels.cu siglip_kernels.cuh siglip_capi.cu; do git show b304770:distributed_sigmoid_loss_b200/csrc/$f > /tmp/r1/distributed_sigmoid_loss_b200/csrc/$f; done;
+         git show b304770:include/siglip_b200.h > /tmp/r1/include/siglip_b200.h;
+         (cd /tmp/r1/distributed_sigmoid_loss_b200/csrc && nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -Xcompiler -fPIC -shared
+          -o <repo>/tools/_r1_libsiglip_b200.so siglip_kernels.cu siglip_capi.cu)
+Interleaved A/B of that library (tools/_r1_libsiglip_b200.so, built from git b304770) against the current one
 on the same GPU in the same process: siglip_fwd_bwd at one shape, alternating ~0.25 s blocks in the sustained
 (power-capped) state, kernel times from the libraries' own CUDA-event brackets (SIGLIP_OPT_KERNEL_TIMING)."""
 import argparse
