@@ -104,8 +104,10 @@ int siglip_device_count(void);
 /*
  * Create the per-process context: replaces DDPSigmoidLoss.__init__ (distributed_sigmoid_loss.py:9-15) —
  * `B` is its gpu_batch_size, `rank`/`world` what dist.get_rank()/get_world_size() return at :37-38.
- * Allocates the workspaces (gathered text [world*B, D] bf16, per-owner dtxt slots [world][B, D] fp32, fp16 operand
- * copies, reduction partials, flags; the [Bp, Bp] 16-bit sigma operands — one per text chunk — on first use). `device` is the CUDA device ordinal.
+ * Allocates the workspaces (gathered text [world*B, D] bf16, per-owner dtxt slots [world][B, D] fp32, reduction partials,
+ * flags); the [Bp, Bp] 16-bit sigma operands and the fp16 text copies that go with them are allocated on first use: two for
+ * the fused step whatever the world size, one per rank for the split forward / backward API (an allocation failure there
+ * says how many GiB were needed). On any failure nothing stays allocated. `device` is the CUDA device ordinal.
  */
 int siglip_ctx_create(siglip_ctx** out, int device, int rank, int world, int B, int D);
 

@@ -17,6 +17,7 @@ ap.add_argument("--B", type=int, default=4096)
 ap.add_argument("--D", type=int, default=768)
 ap.add_argument("--steps", type=int, default=40)
 ap.add_argument("--pdl", type=int, default=1)
+ap.add_argument("--split-k", type=int, default=0)
 a = ap.parse_args()
 dev = torch.device("cuda", 0)
 g = torch.Generator().manual_seed(1234)
@@ -25,7 +26,7 @@ txt = torch.nn.functional.normalize(torch.randn(a.B, a.D, generator=g)).to(torch
 tp = torch.tensor([math.log(10.0)], device=dev)
 b = torch.tensor([-10.0], device=dev)
 eng = SigmoidLossEngine(a.B, a.D, dev)
-eng.set_option(_capi.SIGLIP_OPT_SPLIT_K, 0)
+eng.set_option(_capi.SIGLIP_OPT_SPLIT_K, a.split_k)
 eng.set_option(_capi.SIGLIP_OPT_PDL, a.pdl)
 for _ in range(20):
     eng.fwd_bwd(img, txt, tp, b, torch.bfloat16)
