@@ -427,9 +427,27 @@ def run_ours(args):
             loss = mod(img, txt)
             loss.backward()
             return loss
-    else:   # the fused C-ABI entry siglip_fwd_bwd (BASELINE.json configs[1] "fused fwd+bwd"), bf16 gradients
+    elif args.api == "fused":   # the fused C-ABI entry siglip_fwd_bwd (BASELINE.json configs[1] "fused fwd+bwd"), bf16 gradients
         def step():
             return eng.fwd_bwd(img_d, txt_d, tpt, bt, torch.bfloat16)[0]
+    else:   # the same fused C-ABI step captured once into a CUDA graph and replayed (single rank only: the cross-rank
+            # flag values of a multi-rank step are kernel parameters that advance every step)
+        if world > 1:
+            raise SystemExit("--api graph is a single-GPU measurement")
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.stream(side):
+            eng.fwd_bwd(img_d, txt_d, tpt, bt, torch.bfloat16)
+            n_before = eng.launch_count
+            with torch.cuda.graph(graph, stream=side):
+                graph_out = eng.fwd_bwd(img_d, txt_d, tpt, bt, torch.bfloat16)
+            graph_launches = eng.launch_count - n_before      # kernel nodes of the graph (2: loss + gradient kernel)
+        torch.cuda.current_stream().wait_stream(side)
+
+        def step():
+            graph.replay()
+            return graph_out[0]
 
     def barrier():
         if world > 1:
@@ -499,6 +517,8 @@ def run_ours(args):
         ms_total = float(t)
     ms_step = ms_total / args.steps
     launches = eng.launch_count - launches0
+    if args.api == "graph":
+        launches = graph_launches * args.steps                # replays launch the captured kernel nodes
     value = W * B / (ms_step * 1e-3)
     # Second timed region, right behind the first, same K steps: every loss / gradient launch bracketed by CUDA events on
     # the launch stream (the per-kernel durations of the roofline). Kept apart from the value above because an event
@@ -508,7 +528,10 @@ def run_ours(args):
     k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     k0.record()
     for _ in range(args.steps):
-        step()
+        if args.api == "graph":       # events cannot sit inside a replay: the per-kernel times come from eager fused steps
+            eng.fwd_bwd(img_d, txt_d, tpt, bt, torch.bfloat16)
+        else:
+            step()
     k1.record()
     barrier()
     ms_step_events = k0.elapsed_time(k1) / args.steps
@@ -648,9 +671,11 @@ def run_ours(args):
                              if B >= 8192 else "no explicit flush: inputs + sigma operand of a step fit the 126 MB L2 at this "
                                                "shape (as they do in a training loop that calls the loss every step)",
                        "api": "DDPSigmoidLoss.forward + loss.backward() (torch autograd over the C ABI)"
-                              if args.api == "module" else "siglip_fwd_bwd (C ABI, one fused call, bf16 gradients)",
+                              if args.api == "module" else ("siglip_fwd_bwd (C ABI, one fused call, bf16 gradients)"
+                                                            if args.api == "fused" else
+                                                            "CUDA graph of one siglip_fwd_bwd step, replayed"),
                        "schedule": ("fused step: L0 L1 G1 ... G0, two sigma operands, cross-rank flags inside the kernels"
-                                    if (fused_step or (fused_step is None and W > 1) or args.api == "fused") else
+                                    if (fused_step or (fused_step is None and W > 1) or args.api != "module") else
                                     "split: W loss kernels in forward(), W gradient kernels in backward()")},
             "loss": float(loss.detach().reshape(-1)[0]),
             "parity": parity,
@@ -749,8 +774,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=16384)
     ap.add_argument("--dim", type=int, default=1024)
-    ap.add_argument("--api", default="module", choices=["module", "fused"],
-                    help="what one timed step calls: the nn.Module (forward + backward) or the fused C-ABI entry")
+    ap.add_argument("--api", default="module", choices=["module", "fused", "graph"],
+                    help="what one timed step calls: the nn.Module (forward + backward), the fused C-ABI entry, or a CUDA "
+                         "graph of the fused C-ABI step (single GPU)")
     ap.add_argument("--schedule", default="auto", choices=["auto", "fused", "split"],
                     help="module schedule: auto = fused step (two sigma operands, in-kernel flags) on a multi-rank group and "
                          "split forward/backward on one rank; fused / split force one")

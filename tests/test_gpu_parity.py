@@ -1192,3 +1192,39 @@ def test_t_prime_is_taken_in_the_references_own_dtype():
     assert abs(float(d64[2]) - 2.0 * float(r32[3])) <= 1e-6 * abs(float(r32[3]))
     assert torch.equal(r32b[1], r32[1]) and torch.equal(r32b[3], r32[3])
     eng.close()
+
+
+def test_fused_step_is_cuda_graph_capturable():
+    """The fused single-rank step is two stream-ordered launches with no host synchronisation, no allocation after the
+    first call and kernel parameters passed by value (tensor maps are __grid_constant__): it can be captured into a CUDA
+    graph and replayed; replays reproduce the eager results bit for bit and follow the inputs' CONTENT (same buffers)."""
+    B, D = 1024, 256
+    eng = _engine(B, D, 2)
+    img, txt = _synth(B, D, seed=31)
+    img2, txt2 = _synth(B, D, seed=32)
+    tp, b = _scal(math.log(10.0)), _scal(-10.0)
+    eager1 = [x.clone() for x in eng.fwd_bwd(img, txt, tp, b, torch.bfloat16)]
+    eager2 = [x.clone() for x in eng.fwd_bwd(img2, txt2, tp, b, torch.bfloat16)]
+    si, st_ = img.clone(), txt.clone()                  # static input buffers of the graph
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        eng.fwd_bwd(si, st_, tp, b, torch.bfloat16)      # warm-up on the capture stream
+        with torch.cuda.graph(g, stream=side):
+            outs = eng.fwd_bwd(si, st_, tp, b, torch.bfloat16)
+    torch.cuda.current_stream().wait_stream(side)
+    g.replay()
+    torch.cuda.synchronize()
+    for a, e in zip(outs, eager1):
+        assert torch.equal(a, e)
+    si.copy_(img2)
+    st_.copy_(txt2)
+    g.replay()
+    g.replay()
+    torch.cuda.synchronize()
+    for a, e in zip(outs, eager2):
+        assert torch.equal(a, e)
+    del g
+    eng.close()
