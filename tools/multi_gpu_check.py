@@ -38,6 +38,10 @@ def main() -> int:
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--all-variants", action="store_true", help="also time the non-overlapped variants")
     ap.add_argument("--skip-parity", action="store_true")
+    ap.add_argument("--soak", type=int, default=0,
+                    help="N > 0: that many back-to-back steps at the --batch/--dim shape mixing the fused step, the split "
+                         "API and forward-only calls; same inputs, so every step of a kind must reproduce its first result "
+                         "bit for bit")
     args = ap.parse_args()
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
@@ -207,6 +211,24 @@ def main() -> int:
         dtp=abs(float(dtp) - ref["dt_prime"]) / abs(ref["dt_prime"]),
         db=abs(float(db) - ref["dbias"]) / abs(ref["dbias"])))
 
+    # ---- a late rank: the last rank arrives 2.5 s after the others; they wait INSIDE their kernels (bounded by
+    # SIGLIP_OPT_PEER_TIMEOUT_MS, minutes by default) and the step still gives the same numbers -----------------------
+    import time
+    dist.barrier()
+    torch.cuda.synchronize()
+    if rank == world - 1:
+        time.sleep(2.5)
+    t0 = time.perf_counter()
+    loss_l, dimg_l, dtxt_l, dtp_l, db_l = eng.fwd_bwd(img, txt, torch.tensor([tp], device=dev),
+                                                      torch.tensor([bias], device=dev))
+    torch.cuda.synchronize()
+    waited = time.perf_counter() - t0
+    report("late rank (2.5 s)", dict(
+        loss=abs(float(loss_l) - ref["loss"]) / abs(ref["loss"]),
+        dimg=rel_f(dimg_l, ref["dimg"]), dtxt=rel_f(dtxt_l, contrib[rank]),
+        bitwise_vs_on_time=0.0 if (torch.equal(dimg_l, dimg) and torch.equal(dtxt_l, dtxt)) else 1.0,
+        waited_too_little=0.0 if (rank == world - 1 or waited > 2.0) else 1.0))
+
     # ---- mean over ranks of the scalar gradients inside the backward (no DDP wrapper needed) -----
     both = torch.stack([dtp.reshape(()), db.reshape(())]).double()
     dist.all_reduce(both)
@@ -286,6 +308,44 @@ def main() -> int:
             timed(eng, "in-kernel pull, reduction at the end")
             eng.set_option(_capi.SIGLIP_OPT_OVERLAP_PULL, 0)
             timed(eng, "separate copy, reduction at the end")
+    # ---- soak: thousands of steps through the cross-rank protocol (monotonic flags, tickets, buffer hand-over) --------
+    if args.soak > 0:
+        B, D = args.batch, args.dim
+        g = torch.Generator().manual_seed(4321 + rank)
+        img = torch.nn.functional.normalize(torch.randn(B, D, generator=g)).to(torch.bfloat16).to(dev)
+        txt = torch.nn.functional.normalize(torch.randn(B, D, generator=g)).to(torch.bfloat16).to(dev)
+        mod = DDPSigmoidLoss(B).to(dev)
+        eng = mod.engine_for(B, D, dev)
+        tpt, bt = torch.tensor([math.log(10.0)], device=dev), torch.tensor([-10.0], device=dev)
+        first = {}
+        bad = 0
+        import time
+        dist.barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        pattern = ["fused", "fused", "fused", "split", "fused", "fwd", "fused", "fused"]
+        for i in range(args.soak):
+            kind = pattern[i % len(pattern)]
+            if kind == "fused":
+                out = eng.fwd_bwd(img, txt, tpt, bt, torch.bfloat16)
+                res = (out[0], out[1], out[2], out[3], out[4])
+            elif kind == "split":
+                l_ = eng.forward(img, txt, tpt, bt, True)
+                d_ = eng.backward(img, txt, tpt, None, torch.bfloat16)
+                res = (l_, d_[0], d_[1], d_[2], d_[3])
+            else:
+                res = (eng.fwd(img, txt, tpt, bt),)
+            if kind not in first:
+                first[kind] = [x.clone() for x in res]
+            elif i % 97 == 0 or i >= args.soak - len(pattern):      # spot checks + the last round of every kind
+                bad += sum(0 if torch.equal(a, b) else 1 for a, b in zip(res, first[kind]))
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        same = all(torch.equal(a, b) for a, b in zip(first["fused"][:5], first["split"][:5]))
+        report(f"soak {args.soak} steps B={B} D={D} ({dt:.1f} s)", dict(
+            steps_that_differ_from_their_first=float(bad), fused_vs_split_not_bitwise=0.0 if same else 1.0), tol=0.5)
+        eng.close()
+
     flag = torch.tensor([0 if ok else 1], device=dev)
     dist.all_reduce(flag)
     dist.barrier()
