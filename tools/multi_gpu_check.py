@@ -341,9 +341,16 @@ def main() -> int:
                 bad += sum(0 if torch.equal(a, b) else 1 for a, b in zip(res, first[kind]))
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
-        same = all(torch.equal(a, b) for a, b in zip(first["fused"][:5], first["split"][:5]))
+        # fused vs split schedule: loss, dimg and the scalars are the same arithmetic (bitwise); the text gradient adds the
+        # same fp32 terms, the fused step with one rounding less (own term and folded peer sum meet in one fma of the
+        # last gradient kernel's epilogue instead of a separate add): equal to the last bit or two, not bitwise
+        f_, s_ = first["fused"], first["split"]
+        same = all(torch.equal(f_[i], s_[i]) for i in (0, 1, 3, 4))
         report(f"soak {args.soak} steps B={B} D={D} ({dt:.1f} s)", dict(
-            steps_that_differ_from_their_first=float(bad), fused_vs_split_not_bitwise=0.0 if same else 1.0), tol=0.5)
+            steps_that_differ_from_their_first=float(bad), fused_vs_split_not_bitwise=0.0 if same else 1.0,
+            fused_vs_split_dtxt=rel_f(f_[2].float(), s_[2].float()) * 1e4), tol=0.5)
+        # (x 1e4: the bf16 text gradients of the two schedules within 5e-5 relative Frobenius — an fp32 last-bit
+        # difference flips the bf16 rounding of about one element in 2^16: measured 1.2e-5)
         eng.close()
 
     flag = torch.tensor([0 if ok else 1], device=dev)
