@@ -189,3 +189,16 @@ def test_module_pads_odd_widths_and_copies_views_without_a_gpu():
     v = base[:, 3:11]
     a = _aligned(v)
     assert a.is_contiguous() and a.data_ptr() % 16 == 0 and torch.equal(a, v)
+
+
+def test_option_and_status_constants_match_the_header():
+    """The ctypes binding repeats the enum values of include/siglip_b200.h: a renumbered or missing option would silently
+    set the wrong knob."""
+    text = open(os.path.join(ROOT, "include", "siglip_b200.h")).read()
+    declared = dict((m.group(1), int(m.group(2))) for m in re.finditer(r"\b(SIGLIP_(?:OPT|ERR)_[A-Z0-9_]+|SIGLIP_OK)\s*=\s*(\d+)", text))
+    assert len([k for k in declared if k.startswith("SIGLIP_OPT_")]) >= 20
+    for name, value in declared.items():
+        assert hasattr(_capi, name), f"{name} is declared in the header but missing from _capi.py"
+        assert getattr(_capi, name) == value, (name, getattr(_capi, name), value)
+    values = [v for k, v in declared.items() if k.startswith("SIGLIP_OPT_")]
+    assert len(values) == len(set(values)), "two options share a number"
