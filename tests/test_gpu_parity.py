@@ -1228,3 +1228,40 @@ def test_fused_step_is_cuda_graph_capturable():
         assert torch.equal(a, e)
     del g
     eng.close()
+
+
+def test_fused_schedule_composes_with_normalisation_and_the_siglip_adapter():
+    """The fused schedule (default on multi-rank groups) through the two other module surfaces: fused L2 normalisation
+    (fp32 gradients of the normalised embeddings, then the projection) and the open_clip-signature adapter — same
+    numbers as the split schedule."""
+    from distributed_sigmoid_loss_b200 import DDPSigmoidLoss, SigLipLoss
+    B, D = 512, 192
+    g = torch.Generator().manual_seed(8)
+    x = (torch.randn(B, D, generator=g) * 2.0 + 0.1).to(_dev())
+    y = (torch.randn(B, D, generator=g) * 0.7).to(_dev())
+    res = []
+    for fused in (False, True):
+        mod = DDPSigmoidLoss(B, normalize_inputs=True, fused_step=fused).to(_dev())
+        a, b = x.clone().requires_grad_(True), y.clone().requires_grad_(True)
+        loss = mod(a, b)
+        (3.0 * loss).backward()
+        torch.cuda.synchronize()
+        res.append((loss.detach(), a.grad, b.grad, mod.t_prime.grad.clone(), mod.bias.grad.clone()))
+    assert torch.equal(res[0][0], res[1][0])
+    _check("d raw img", res[1][1], res[0][1], tol=1e-5)
+    _check("d raw txt", res[1][2], res[0][2], tol=1e-5)
+    _check("dt_prime", res[1][3], float(res[0][3]), tol=1e-6)
+    _check("dbias", res[1][4], float(res[0][4]), tol=1e-6)
+    img, txt = _synth(B, D, seed=12)
+    out = []
+    for fused in (False, True):
+        scale = torch.nn.Parameter(torch.tensor(math.log(10.0), device=_dev()))
+        lbias = torch.nn.Parameter(torch.tensor(-10.0, device=_dev()))
+        a = img.clone().requires_grad_(True)
+        l = SigLipLoss(rank=0, world_size=1, fused_step=fused)(a, txt, scale, lbias)
+        l.backward()
+        torch.cuda.synchronize()
+        out.append((l.detach(), a.grad, scale.grad.clone(), lbias.grad.clone()))
+    assert torch.equal(out[0][0], out[1][0]) and torch.equal(out[0][1], out[1][1])
+    _check("dscale", out[1][2], float(out[0][2]), tol=1e-6)
+    _check("dbias", out[1][3], float(out[0][3]), tol=1e-6)
