@@ -8,8 +8,10 @@ reference itself: ``tests/golden/make_golden.py`` imports the unmodified ``/root
 (``DDPSigmoidLoss`` and ``SigLipLoss`` under gloo) in the build container and commits their outputs as
 fixtures; ``tests/test_oracle.py`` checks both functions below against every fixture.
 
-Two restatements, both following the reference line by line (file:line cited per function):
+Restatements, following the reference line by line (file:line cited per function):
   * ``closed_form``  — float64 numpy, the analytic loss and all four gradients for every rank at once;
+  * ``closed_form_uneven`` — the same for ranks with different batch sizes (an extension the reference cannot run;
+                       pinned on ``closed_form`` for equal batches and on torch autograd otherwise);
   * ``port_step``    — the same sequence of materialised torch ops the reference executes (GEMM, scale, bias,
                        labels, logsigmoid, sum, autograd), one rank, all W chunks; used as the timed CPU baseline.
 """
@@ -70,6 +72,37 @@ def closed_form(img_all: np.ndarray, txt_all: np.ndarray, t_prime: float, bias: 
             dt_prime=float(t * (g[rows] * s[rows]).sum()),
             dbias=float(g[rows].sum()),
         ))
+    return out
+
+
+def closed_form_uneven(img_blocks, txt_blocks, t_prime: float, bias: float) -> List[Dict]:
+    """`closed_form` for ranks with DIFFERENT batch sizes. The reference cannot express this (its
+    labels are gpu_batch_size x gpu_batch_size, distributed_sigmoid_loss.py:26-30, and all_gather needs equal shapes);
+    the semantics extend it where it is defined: rank r scores its B_r images against every rank's texts (:41-45), the
+    positives are the diagonal of its own chunk (:28), and its loss is divided by ITS batch (:47).
+    img_blocks[r]: [B_r, D], txt_blocks[c]: [B_c, D]. Returns per rank: loss, dimg [B_r, D], dt_prime, dbias and
+    contrib[c] = that rank's contribution to the text gradient of chunk c ([B_c, D]); the text gradient rank c ends up
+    with is the sum over ranks of contrib[c] (what the backward of all_gather delivers)."""
+    t = math.exp(t_prime)
+    out = []
+    for r, img in enumerate(img_blocks):
+        img = np.asarray(img, dtype=np.float64)
+        br = img.shape[0]
+        res = dict(loss=0.0, dimg=np.zeros_like(img), dt_prime=0.0, dbias=0.0, contrib=[])
+        for c, txt in enumerate(txt_blocks):
+            txt = np.asarray(txt, dtype=np.float64)
+            s = img @ txt.T
+            z = t * s + bias
+            y = -np.ones_like(z)
+            if c == r:
+                y[np.arange(br), np.arange(br)] = 1.0
+            g = -y * _sigmoid(-y * z) / br
+            res["loss"] += float(_softplus(-y * z).sum() / br)
+            res["dimg"] += t * (g @ txt)
+            res["contrib"].append(t * (g.T @ img))
+            res["dt_prime"] += float(t * (g * s).sum())
+            res["dbias"] += float(g.sum())
+        out.append(res)
     return out
 
 

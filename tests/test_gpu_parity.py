@@ -884,35 +884,6 @@ def test_d1152_sweep_against_both_reference_variants(name):
 # ---------------------------------------------------------------------------------------------------------
 # uneven per-rank batch
 # ---------------------------------------------------------------------------------------------------------
-def _uneven_closed_form(img_blocks, txt_blocks, tp, bias):
-    """float64 closed form for ranks with different batches (distributed_sigmoid_loss.py:22-47 semantics where they
-    are defined: rank r sums its B_r images against all texts and divides by ITS batch; labels +1 on the own chunk's
-    diagonal). Returns per rank: loss, dimg, dt', db, and contrib[r][c] = rank r's contribution to chunk c's dtxt."""
-    t = math.exp(tp)
-    out = []
-    for r, img in enumerate(img_blocks):
-        img = img.astype(np.float64)
-        br = img.shape[0]
-        res = dict(loss=0.0, dimg=np.zeros_like(img), dtp=0.0, db=0.0, contrib=[])
-        for c, txt in enumerate(txt_blocks):
-            txt = txt.astype(np.float64)
-            s = img @ txt.T
-            z = t * s + bias
-            y = -np.ones_like(z)
-            if c == r:
-                y[np.arange(br), np.arange(br)] = 1.0
-            e = np.exp(-np.abs(-y * z))
-            sig = np.where(-y * z >= 0, 1.0 / (1.0 + e), e / (1.0 + e))        # sigma(-y z)
-            g = -y * sig / br
-            res["loss"] += float((np.maximum(-y * z, 0.0) + np.log1p(e)).sum() / br)
-            res["dimg"] += t * (g @ txt)
-            res["contrib"].append(t * (g.T @ img))
-            res["dtp"] += float(t * (g * s).sum())
-            res["db"] += float(g.sum())
-        out.append(res)
-    return out
-
-
 def test_uneven_per_rank_batches_loopback():
     """Ranks with B = (40, 24, 33) (siglip_ctx_create_uneven): every rank replayed on one GPU; per-rank loss / dimg /
     scalars and the per-owner dtxt sums against the float64 closed form."""
@@ -922,7 +893,8 @@ def test_uneven_per_rank_batches_loopback():
     g = torch.Generator().manual_seed(31)
     imgs = [torch.nn.functional.normalize(torch.randn(b, D, generator=g)).to(torch.bfloat16) for b in Bs]
     txts = [torch.nn.functional.normalize(torch.randn(b, D, generator=g)).to(torch.bfloat16) for b in Bs]
-    ref = _uneven_closed_form([x.float().numpy() for x in imgs], [x.float().numpy() for x in txts], tp, bias)
+    from oracle.siglip_oracle import closed_form_uneven
+    ref = closed_form_uneven([x.float().numpy() for x in imgs], [x.float().numpy() for x in txts], tp, bias)
     for sched in ("fused", "split"):
         dtxt_sum = [torch.zeros(b, D, device=_dev()) for b in Bs]
         for r in range(W):
@@ -938,8 +910,8 @@ def test_uneven_per_rank_batches_loopback():
             torch.cuda.synchronize()
             _check(f"{sched} loss r{r}", loss, ref[r]["loss"])
             _check(f"{sched} dimg r{r}", dimg, ref[r]["dimg"])
-            _check(f"{sched} dt_prime r{r}", dtp, ref[r]["dtp"])
-            _check(f"{sched} dbias r{r}", db, ref[r]["db"])
+            _check(f"{sched} dt_prime r{r}", dtp, ref[r]["dt_prime"])
+            _check(f"{sched} dbias r{r}", db, ref[r]["dbias"])
             for k in range(W):
                 got = _contribution(eng, k, dtxt)
                 assert tuple(got.shape) == (Bs[k], D)

@@ -1,5 +1,7 @@
 """The oracle (oracle/siglip_oracle.py) against the golden fixtures produced by the unmodified reference
 (tests/golden/make_golden.py). CPU only."""
+import math
+
 import numpy as np
 import pytest
 import torch
@@ -127,3 +129,46 @@ def test_closed_form_equals_port_on_random_problems():
             assert _close(dtxt_sum[r * B:(r + 1) * B].numpy(), out[r]["dtxt"], rel=1e-9, abs_=1e-12)
 
     check()
+
+
+def test_uneven_closed_form_reduces_to_the_pinned_one_and_matches_autograd():
+    """closed_form_uneven (used by the GPU tests of siglip_ctx_create_uneven) is pinned twice: for equal batches it must
+    reproduce closed_form — itself pinned on the reference's fixtures — and for unequal ones torch autograd of the
+    reference's op sequence with per-rank labels."""
+    import torch
+
+    from oracle.siglip_oracle import closed_form, closed_form_uneven
+
+    rng = np.random.default_rng(5)
+    W, B, D = 3, 7, 12
+    img = rng.standard_normal((W * B, D))
+    txt = rng.standard_normal((W * B, D))
+    img /= np.linalg.norm(img, axis=1, keepdims=True)
+    txt /= np.linalg.norm(txt, axis=1, keepdims=True)
+    tp, bias = math.log(9.0), -6.0
+    eq = closed_form(img, txt, tp, bias, W)
+    un = closed_form_uneven([img[r * B:(r + 1) * B] for r in range(W)], [txt[c * B:(c + 1) * B] for c in range(W)], tp, bias)
+    for r in range(W):
+        assert abs(un[r]["loss"] - eq[r]["loss"]) < 1e-12 and np.allclose(un[r]["dimg"], eq[r]["dimg"], atol=1e-14)
+        assert abs(un[r]["dt_prime"] - eq[r]["dt_prime"]) < 1e-12 and abs(un[r]["dbias"] - eq[r]["dbias"]) < 1e-12
+        assert np.allclose(sum(un[q]["contrib"][r] for q in range(W)), eq[r]["dtxt"], atol=1e-14)
+    Bs = (5, 9, 3)
+    imgs = [rng.standard_normal((b, D)) for b in Bs]
+    txts = [rng.standard_normal((b, D)) for b in Bs]
+    un = closed_form_uneven(imgs, txts, tp, bias)
+    for r, b in enumerate(Bs):
+        a = torch.tensor(imgs[r], requires_grad=True)
+        ts = [torch.tensor(x, requires_grad=True) for x in txts]
+        t_ = torch.tensor(tp, dtype=torch.float64, requires_grad=True)
+        b_ = torch.tensor(bias, dtype=torch.float64, requires_grad=True)
+        total = 0
+        for c, tx in enumerate(ts):
+            logits = a @ tx.T * t_.exp() + b_
+            labels = 2 * torch.eye(b, dtype=torch.float64) - 1 if c == r else -torch.ones(Bs[c], dtype=torch.float64)
+            total = total + (-torch.nn.functional.logsigmoid(labels * logits)).sum()
+        (total / b).backward()
+        assert abs(float(total / b) - un[r]["loss"]) < 1e-10
+        assert np.allclose(a.grad.numpy(), un[r]["dimg"], atol=1e-12)
+        assert abs(float(t_.grad) - un[r]["dt_prime"]) < 1e-10 and abs(float(b_.grad) - un[r]["dbias"]) < 1e-10
+        for c in range(W):
+            assert np.allclose(ts[c].grad.numpy(), un[r]["contrib"][c], atol=1e-12)
