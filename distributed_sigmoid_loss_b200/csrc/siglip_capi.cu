@@ -602,11 +602,19 @@ inline EndSignal end_signal(siglip_ctx* c, int kind, unsigned int value) {
   return e;
 }
 
-int check_call(siglip_ctx* c, const void* img, const void* txt, const float* t_prime) {
+int check_call(siglip_ctx* c, const void* img, const void* txt, const float* t_prime, cudaStream_t st) {
   if (c == nullptr || img == nullptr || txt == nullptr || t_prime == nullptr)
     return fail(SIGLIP_ERR_INVALID, "null argument");
   if (c->world > 1 && !c->peers_ready)
     return fail(SIGLIP_ERR_STATE, "world > 1 but peer handles were not imported (siglip_ctx_import_handles)");
+  if (c->world > 1) {
+    // a multi-rank step cannot be replayed from a CUDA graph: the flag values its kernels wait for / raise are kernel
+    // parameters that advance with every step (a single-rank step has none and captures fine)
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(st, &cs) == cudaSuccess && cs != cudaStreamCaptureStatusNone)
+      return fail(SIGLIP_ERR_STATE,
+                  "a multi-rank step cannot be captured into a CUDA graph (its cross-rank flag values advance every step)");
+  }
   return 0;
 }
 
@@ -631,7 +639,7 @@ void add_pull_job(siglip_ctx* c, AuxList& aux, int o, unsigned int s) {
 int forward_impl(siglip_ctx* c, const void* img, const void* txt, const float* t_prime, const float* bias, float* loss,
                  bool save, cudaStream_t st) {
   int rc;
-  if ((rc = check_call(c, img, txt, t_prime))) return rc;
+  if ((rc = check_call(c, img, txt, t_prime, st))) return rc;
   if (bias == nullptr || loss == nullptr) return fail(SIGLIP_ERR_INVALID, "null argument");
   if ((rc = check_dbg(c, "siglip forward (previous launch)"))) return rc;
   CK(cudaSetDevice(c->device));
@@ -700,7 +708,7 @@ int forward_impl(siglip_ctx* c, const void* img, const void* txt, const float* t
 int backward_impl(siglip_ctx* c, const void* img, const void* txt, const float* t_prime, const float* grad_out,
                   void* dimg, void* dtxt, float* dt_prime, float* dbias, cudaStream_t st) {
   int rc;
-  if ((rc = check_call(c, img, txt, t_prime))) return rc;
+  if ((rc = check_call(c, img, txt, t_prime, st))) return rc;
   if (dimg == nullptr || dtxt == nullptr) return fail(SIGLIP_ERR_INVALID, "null argument");
   if (c->gen == 0) return fail(SIGLIP_ERR_STATE, "no forward state saved for backward (call siglip_forward with save = 1)");
   if ((rc = check_dbg(c, "siglip backward (previous launch)"))) return rc;
@@ -793,7 +801,7 @@ int backward_impl(siglip_ctx* c, const void* img, const void* txt, const float* 
 int fused_impl(siglip_ctx* c, const void* img, const void* txt, const float* t_prime, const float* bias, float* loss,
                const float* grad_out, void* dimg, void* dtxt, float* dt_prime, float* dbias, cudaStream_t st) {
   int rc;
-  if ((rc = check_call(c, img, txt, t_prime))) return rc;
+  if ((rc = check_call(c, img, txt, t_prime, st))) return rc;
   if (bias == nullptr || loss == nullptr || dimg == nullptr || dtxt == nullptr)
     return fail(SIGLIP_ERR_INVALID, "null argument");
   if ((rc = check_dbg(c, "siglip_fwd_bwd (previous launch)"))) return rc;

@@ -146,6 +146,8 @@ int siglip_ctx_import_handles(siglip_ctx* ctx, const void* all_ranks_bytes, size
  * Loss and gradient kernels alternate chunk by chunk (L0 L1 G1 L2 G2 ... G0), so only TWO [B, B] sigma operands exist
  * however many ranks there are (the split siglip_forward / siglip_backward keep one per rank between the two calls),
  * and every cross-rank flag is waited for / raised inside the kernels: a W-rank step is exactly 2W launches.
+ * A single-rank step performs no host synchronisation and no allocation after the first call and can be captured into a
+ * CUDA graph; a multi-rank step cannot (its flag values advance every step) and returns SIGLIP_ERR_STATE under capture.
  */
 int siglip_fwd_bwd(siglip_ctx* ctx, const void* img, const void* txt, const float* t_prime, const float* bias,
                    float* loss, void* dimg, void* dtxt, float* dt_prime, float* dbias, void* cuda_stream);

@@ -1237,3 +1237,33 @@ def test_fused_schedule_composes_with_normalisation_and_the_siglip_adapter():
     assert torch.equal(out[0][0], out[1][0]) and torch.equal(out[0][1], out[1][1])
     _check("dscale", out[1][2], float(out[0][2]), tol=1e-6)
     _check("dbias", out[1][3], float(out[0][3]), tol=1e-6)
+
+
+def test_multi_rank_step_refuses_graph_capture():
+    B, D = 256, 64
+    img, txt = _synth(B, D)
+    eng = _engine(B, D, 2, rank_world=(0, 2), loopback=True)
+    eng.debug_set_text_chunk(0, txt)
+    eng.debug_set_text_chunk(1, txt)
+    tp, b = _scal(1.0), _scal(-5.0)
+    eng.fwd_bwd(img, txt, tp, b)
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    raised = False
+    with torch.cuda.stream(side):
+        try:
+            with torch.cuda.graph(g, stream=side):
+                try:
+                    eng.fwd_bwd(img, txt, tp, b)
+                except RuntimeError as ex:
+                    raised = "cannot be captured" in str(ex)
+        except Exception:       # an empty / aborted capture may itself complain: irrelevant here
+            pass
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    assert raised
+    eng.fwd_bwd(img, txt, tp, b)                          # the context is still usable
+    torch.cuda.synchronize()
+    eng.close()
