@@ -211,6 +211,42 @@ def main() -> int:
         dtp=abs(float(dtp) - ref["dt_prime"]) / abs(ref["dt_prime"]),
         db=abs(float(db) - ref["dbias"]) / abs(ref["dbias"])))
 
+    # ---- the reference's own acceptance test on GPUs: encoder-weight gradients of the W-rank job, averaged over the
+    # ranks, equal those of ONE rank holding the whole batch (test_distributed_sigmoid_loss.py:122-141 test_same_gradient;
+    # toy linear encoders :71-77, seeds 42 / 40 and the row partition :55-68, gradient averaging :79-83). fp32 leaves,
+    # like the reference feeds them; output widths 64 and the reference's own 2 (padded to 8 inside the module) ----------
+    if not args.skip_parity:
+        groups = [dist.new_group([q]) for q in range(world)]       # collective: every rank creates every 1-rank group
+        for out_dim in (64, 2):
+            in_dim, bpr = 32, 32
+            torch.manual_seed(42)
+            x_img = torch.randn(world * bpr, in_dim)
+            torch.manual_seed(40)
+            x_txt = torch.randn(world * bpr, in_dim)
+
+            def run(rows, group, batch):
+                torch.manual_seed(42)
+                enc_i = torch.nn.Linear(in_dim, out_dim, bias=False).to(dev)
+                torch.manual_seed(42)
+                enc_t = torch.nn.Linear(in_dim, out_dim, bias=False).to(dev)
+                mod_ = DDPSigmoidLoss(batch, group=group).to(dev)
+                e_i = torch.nn.functional.normalize(enc_i(x_img[rows].to(dev)))
+                e_t = torch.nn.functional.normalize(enc_t(x_txt[rows].to(dev)))
+                mod_(e_i, e_t).backward()
+                return [enc_i.weight.grad, enc_t.weight.grad, mod_.t_prime.grad.float().reshape(1),
+                        mod_.bias.grad.reshape(1)]
+
+            multi = run(slice(rank * bpr, (rank + 1) * bpr), None, bpr)
+            for gr in multi:                                        # average_gradients
+                dist.all_reduce(gr)
+                gr /= world
+            single = run(slice(0, world * bpr), groups[rank], world * bpr)
+            torch.cuda.synchronize()
+            report(f"same_gradient (reference's test) out_dim={out_dim}", dict(
+                img_encoder=rel_f(multi[0], single[0]), txt_encoder=rel_f(multi[1], single[1]),
+                t_prime=abs(float(multi[2]) - float(single[2])) / abs(float(single[2])),
+                bias=abs(float(multi[3]) - float(single[3])) / abs(float(single[3]))))
+
     # ---- a late rank: the last rank arrives 2.5 s after the others; they wait INSIDE their kernels (bounded by
     # SIGLIP_OPT_PEER_TIMEOUT_MS, minutes by default) and the step still gives the same numbers -----------------------
     import time
