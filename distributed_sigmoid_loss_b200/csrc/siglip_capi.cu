@@ -198,7 +198,7 @@ struct siglip_ctx {
   float* loop_mailboxes = nullptr;       // loopback only: [world][2] stand-ins for the peers' (dt', dbias) mailboxes
   float* loop_zero = nullptr;            // loopback only: [world][Bmax, D] zeros standing in for the peers' contribution slots
   float* scalars = nullptr;              // [24] device scalars: host API staging, saved dt'/dbias of the last forward
-  unsigned long long* aux_trace = nullptr;  // [kTraceLaunches][12] globaltimer stamps (SIGLIP_OPT_AUX_TRACE)
+  unsigned long long* aux_trace = nullptr;  // [kTraceLaunches][16] globaltimer stamps (SIGLIP_OPT_AUX_TRACE)
   float* splitk_ws = nullptr;            // fp32 partial accumulators of the split tiles of the gradient kernel
   unsigned int* splitk_counters = nullptr;  // per split tile: arrivals of the non-owner parts (monotonic)
   size_t splitk_ws_bytes = 0;
@@ -342,7 +342,7 @@ void apply_aux(siglip_ctx* c, KernelParams& p, const AuxList& aux, const EndSign
     p.end_ticket = c->sync_words + kSyncEndTicket;
   }
   if (c->aux_trace_on && c->aux_trace != nullptr && c->aux_trace_n < kTraceLaunches) {
-    p.aux_trace = c->aux_trace + 12ull * c->aux_trace_n;
+    p.aux_trace = c->aux_trace + 16ull * c->aux_trace_n;
     c->aux_trace_n++;
   }
 }
@@ -1150,11 +1150,12 @@ int siglip_ctx_set_option(siglip_ctx* c, int option, int value) {
       c->aux_trace_n = 0;
       if (value && c->aux_trace == nullptr) {
         CK(cudaSetDevice(c->device));
-        CK(cudaMalloc(reinterpret_cast<void**>(&c->aux_trace), kTraceLaunches * 12 * sizeof(unsigned long long)));
+        CK(cudaMalloc(reinterpret_cast<void**>(&c->aux_trace), kTraceLaunches * 16 * sizeof(unsigned long long)));
       }
       if (value) {
-        std::vector<unsigned long long> init(static_cast<size_t>(kTraceLaunches) * 12, 0ull);
-        for (unsigned int i = 0; i < kTraceLaunches; ++i) init[12ull * i + 8] = init[12ull * i + 10] = ~0ull;  // minima
+        std::vector<unsigned long long> init(static_cast<size_t>(kTraceLaunches) * 16, 0ull);
+        for (unsigned int i = 0; i < kTraceLaunches; ++i)
+          init[16ull * i + 8] = init[16ull * i + 10] = init[16ull * i + 13] = ~0ull;  // minima
         CK(cudaMemcpy(c->aux_trace, init.data(), init.size() * sizeof(unsigned long long), cudaMemcpyHostToDevice));
       }
       return 0;
@@ -1514,7 +1515,7 @@ int siglip_ctx_aux_trace(siglip_ctx* c, unsigned long long* out, int max_launche
   CK(cudaDeviceSynchronize());
   int n = static_cast<int>(c->aux_trace_n);
   if (n > max_launches) n = max_launches;
-  if (n > 0) CK(cudaMemcpy(out, c->aux_trace, static_cast<size_t>(n) * 12 * sizeof(unsigned long long),
+  if (n > 0) CK(cudaMemcpy(out, c->aux_trace, static_cast<size_t>(n) * 16 * sizeof(unsigned long long),
                            cudaMemcpyDeviceToHost));
   *n_launches = n;
   c->aux_trace_n = 0;

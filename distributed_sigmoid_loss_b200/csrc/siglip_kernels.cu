@@ -480,7 +480,12 @@ siglip_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_consta
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  if (p.aux_trace != nullptr && blockIdx.x == 0 && threadIdx.x == 0) p.aux_trace[4] = globaltimer_ns();   // kernel entry
+  if (p.aux_trace != nullptr && threadIdx.x == 0) {
+    const unsigned long long now = globaltimer_ns();
+    if (blockIdx.x == 0) p.aux_trace[4] = now;                                       // kernel entry (CTA 0)
+    atomicMax(p.aux_trace + 12, now);                                                // ... of the last CTA to start
+    atomicMin(p.aux_trace + 13, now);                                                // ... of the first
+  }
   static_assert(kMC == 1 || kMC == 2, "operand multicast across 1 or 2 tiles");
   // Cluster layout: kCG consecutive CTAs form one MMA pair; kMC pairs (or single CTAs) on vertically adjacent tiles
   // share the B operand tile by TMA multicast. cg=2, mc=2 is the 2x2 cluster cuBLAS' nvjet kernels use.
@@ -533,7 +538,11 @@ siglip_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_consta
     asm volatile("griddepcontrol.wait;" ::: "memory");
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   }
-  if (p.aux_trace != nullptr && blockIdx.x == 0 && threadIdx.x == 0) p.aux_trace[5] = globaltimer_ns();   // set-up done
+  if (p.aux_trace != nullptr && threadIdx.x == 0) {
+    const unsigned long long now = globaltimer_ns();
+    if (blockIdx.x == 0) p.aux_trace[5] = now;                                       // set-up done (CTA 0)
+    atomicMax(p.aux_trace + 14, now);                                                // ... on the last CTA
+  }
 
   if (warp == kProducerWarp) {
     // ===================================== TMA producer =====================================

@@ -113,12 +113,13 @@ class SigmoidLossEngine:
     def aux_trace(self, max_launches: int = 4096):
         """Per launch since the last call, globaltimer ns: (aux start, flags seen, aux jobs done, launch end, kernel
         entry, set-up done, first operands landed, last MMA issued, first CTA finished, latest / earliest "last MMA issued"
-        over the CTAs, last CTA through its tiles); needs SIGLIP_OPT_AUX_TRACE."""
-        buf = (ctypes.c_ulonglong * (12 * max_launches))()
+        over the CTAs, last CTA through its tiles, last / first CTA to enter the kernel, last CTA through its set-up, unused);
+        needs SIGLIP_OPT_AUX_TRACE."""
+        buf = (ctypes.c_ulonglong * (16 * max_launches))()
         n = ctypes.c_int(0)
         _capi.check(self._L.siglip_ctx_aux_trace(self._h, ctypes.cast(buf, ctypes.c_void_p), max_launches,
                                                  ctypes.byref(n)))
-        return [tuple(int(buf[12 * i + j]) for j in range(12)) for i in range(n.value)]
+        return [tuple(int(buf[16 * i + j]) for j in range(16)) for i in range(n.value)]
 
     @property
     def workspace_bytes(self) -> int:

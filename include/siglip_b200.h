@@ -266,11 +266,12 @@ int siglip_debug_get_slot(siglip_ctx* ctx, int chunk, float* out_dev, void* cuda
 /* Loopback only: seed the (dt_prime, dbias) mailbox standing in for peer rank `peer`, so that the mean computed under
  * SIGLIP_OPT_SYNC_SCALAR_GRADS can be checked against numbers the kernel did not produce itself. */
 int siglip_debug_set_mailbox(siglip_ctx* ctx, int peer, float dt_prime, float dbias);
-/* With SIGLIP_OPT_AUX_TRACE: device-synchronise and copy out 12 globaltimer stamps (ns) per launch since the last call:
+/* With SIGLIP_OPT_AUX_TRACE: device-synchronise and copy out 16 globaltimer stamps (ns) per launch since the last call:
  * [0..2] auxiliary warps of CTA 0: start, last peer flag observed (0 = no wait), jobs done; [3] launch end as seen by
  * the last CTA; [4] kernel entry (CTA 0); [5] set-up done (barriers, TMEM); [6] first operands landed (MMA warp of CTA 0);
  * [7] last MMA issued (CTA 0); [8] first CTA finished; [9] / [10] latest / earliest "last MMA issued" over the CTAs;
- * [11] last CTA through the epilogue of its tiles. `out` holds 12 * max_launches values. */
+ * [11] last CTA through the epilogue of its tiles; [12] / [13] last / first CTA to enter the kernel; [14] last CTA through
+ * its set-up; [15] unused. `out` holds 16 * max_launches values. */
 int siglip_ctx_aux_trace(siglip_ctx* ctx, unsigned long long* out, int max_launches, int* n_launches);
 
 void siglip_ctx_destroy(siglip_ctx* ctx);

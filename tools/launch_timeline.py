@@ -39,11 +39,12 @@ eng.set_option(_capi.SIGLIP_OPT_AUX_TRACE, 0)
 names = ["loss", "grad"]
 acc = {n: [] for n in names}
 for i in range(2, len(tr)):
-    t0, tflag, tdone, tend, tentry, tsetup, tfirst, tlast, tfirstcta, tmma_max, tmma_min, tepi = tr[i]
+    t0, tflag, tdone, tend, tentry, tsetup, tfirst, tlast, tfirstcta, tmma_max, tmma_min, tepi, tent_max, tent_min, \
+        tsetup_max, _ = tr[i]
     prev_end = tr[i - 1][3]
     acc[names[i % 2]].append((tentry - prev_end, tsetup - tentry, tfirst - tsetup, tlast - tfirst, tend - tlast,
                               tend - tentry, tdone - t0, tmma_max - tmma_min, tepi - tmma_max, tend - tepi,
-                              tend - tfirstcta))
+                              tend - tfirstcta, tent_max - tent_min, tsetup_max - tent_min, tend - tent_min))
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 e0.record()
 for _ in range(a.steps):
@@ -53,7 +54,8 @@ torch.cuda.synchronize()
 print(f"pdl={a.pdl}: {e0.elapsed_time(e1) / a.steps * 1e3:.1f} us per fused step (CUDA events around {a.steps} back-to-back steps)")
 print(f"B={a.B} D={a.D}: median over {len(acc['loss'])} launches (us): gap after previous launch | set-up | first operands | "
       "MMA issue span (CTA 0) | tail | kernel entry->end | aux jobs || spread of 'last MMA issued' over CTAs | latest MMA issue -> "
-      "all tiles' epilogues done | -> kernel end | first CTA exit -> kernel end")
+      "all tiles' epilogues done | -> kernel end | first CTA exit -> kernel end || first -> last CTA entry | first entry -> last "
+      "set-up done | first entry -> kernel end")
 for n in names:
     cols = list(zip(*acc[n]))
     med = [sorted(c)[len(c) // 2] / 1e3 for c in cols]
