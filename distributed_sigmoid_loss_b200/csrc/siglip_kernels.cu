@@ -853,7 +853,14 @@ siglip_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_consta
         const int col0 = col_base + c * 32;
         if constexpr (kMode == kModeLoss) {
           const bool sg = p.store_g != 0;
-          if (!edge && !diag) {
+          // Only the 32x32 slabs that touch the diagonal of a diagonal tile (rows and columns are 32-aligned: row0 ==
+          // col0) hold positive pairs, and only the slabs that cross the matrix border of an edge tile need masking:
+          // 8 of the 64 slabs of a diagonal 256x256 tile. Every other slab of such a tile takes the fast path like the
+          // rest of the matrix — a whole diagonal tile on the general path had a 3-4x longer epilogue, which ended up
+          // on the critical path of the clusters that own one (most visible at small B: 16 of 256 tiles at B = 4096).
+          const bool slab_diag = diag && (gst.row0 == col0);
+          const bool slab_edge = edge && ((gst.row0 + 32 > pr.M) || (col0 + 32 > pr.N));
+          if (!slab_edge && !slab_diag) {
             // z is monotone in s (t > 0): the slab is "all very negative" iff max s is
             float smax = fmaxf(__uint_as_float(v[0]), __uint_as_float(v[1]));
 #pragma unroll
@@ -867,7 +874,7 @@ siglip_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_consta
             // edge and / or diagonal tiles (a few per chunk): ONE masked variant — two more copies of the unrolled
             // general path only made the kernel's code larger (the loss and gradient kernels alternate and share the
             // instruction caches)
-            loss_slab<true, true, true>(v, t_eff, bias, row, col0, pr.M, pr.N, sg, gst, p.g_scale, p.g_diag, acc_sp, acc_g, acc_gs, diag);
+            loss_slab<true, true, true>(v, t_eff, bias, row, col0, pr.M, pr.N, sg, gst, p.g_scale, p.g_diag, acc_sp, acc_g, acc_gs, slab_diag);
           }
         } else {
           if (tc.part < 0) {

@@ -23,6 +23,8 @@ ap.add_argument("--D", type=int, default=1024)
 ap.add_argument("--rounds", type=int, default=10)
 ap.add_argument("--block-ms", type=float, default=250.0)
 ap.add_argument("--r2-lib", default=os.path.join(ROOT, "distributed_sigmoid_loss_b200", "libsiglip_b200.so"))
+ap.add_argument("--r1-lib", default=os.path.join(ROOT, "tools", "_r1_libsiglip_b200.so"),
+                help="the library in the 'r1' slot (any earlier build of the same C ABI, e.g. one made from `git show HEAD:...`)")
 ap.add_argument("--fwd-only", action="store_true", help="loss kernel only (siglip_fwd): no gradient kernel in between")
 ap.add_argument("--only", default="", help="r1 or r2: run a few steps of one library only (ncu target)")
 ap.add_argument("--r2-opts", default="", help="comma-separated option=value pairs set on the current library only")
@@ -59,7 +61,7 @@ def apply_opts(L, h):
         assert L.siglip_ctx_set_option(h, int(k), int(v)) == 0, L.siglip_last_error()
 
 
-libs = {"r1": load(os.path.join(ROOT, "tools", "_r1_libsiglip_b200.so")),
+libs = {"r1": load(a.r1_lib),
         "r2": load(a.r2_lib)}
 apply_opts(*libs["r2"])
 st = torch.cuda.current_stream().cuda_stream
