@@ -28,6 +28,8 @@ ap.add_argument("--r1-lib", default=os.path.join(ROOT, "tools", "_r1_libsiglip_b
 ap.add_argument("--fwd-only", action="store_true", help="loss kernel only (siglip_fwd): no gradient kernel in between")
 ap.add_argument("--only", default="", help="r1 or r2: run a few steps of one library only (ncu target)")
 ap.add_argument("--r2-opts", default="", help="comma-separated option=value pairs set on the current library only")
+ap.add_argument("--r1-env", default="", help="comma-separated NAME=VALUE pairs in the environment while the 'r1' context is created")
+ap.add_argument("--r2-env", default="", help="... while the 'r2' context is created (the library reads its SIGLIP_* switches then)")
 a = ap.parse_args()
 dev = torch.device("cuda", 0)
 torch.cuda.set_device(0)
@@ -40,7 +42,18 @@ dtxt = torch.empty(a.B, a.D, device=dev, dtype=torch.bfloat16)
 vp = ctypes.c_void_p
 
 
-def load(path):
+def load(path, env=""):
+    pairs = [kv.split("=") for kv in filter(None, env.split(","))]
+    for k, v in pairs:
+        os.environ[k] = v
+    try:
+        return _load(path)
+    finally:
+        for k, _ in pairs:
+            os.environ.pop(k, None)
+
+
+def _load(path):
     L = ctypes.CDLL(path)
     L.siglip_ctx_create.argtypes = [ctypes.POINTER(vp), ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int]
     L.siglip_ctx_set_option.argtypes = [vp, ctypes.c_int, ctypes.c_int]
@@ -61,8 +74,8 @@ def apply_opts(L, h):
         assert L.siglip_ctx_set_option(h, int(k), int(v)) == 0, L.siglip_last_error()
 
 
-libs = {"r1": load(a.r1_lib),
-        "r2": load(a.r2_lib)}
+libs = {"r1": load(a.r1_lib, a.r1_env),
+        "r2": load(a.r2_lib, a.r2_env)}
 apply_opts(*libs["r2"])
 st = torch.cuda.current_stream().cuda_stream
 p = sc.data_ptr()
