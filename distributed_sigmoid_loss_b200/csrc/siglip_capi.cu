@@ -181,8 +181,6 @@ struct siglip_ctx {
   int aux_trace_on = 0;
   // diagnostics, read from the environment once at context creation (see include/siglip_b200.h)
   bool dbg_no_gstore = false, dbg_no_cvt = false, dbg_loss_waitstats = false;
-  int cvt_mode = 0;                      // fp16 operand copies: 0 in-kernel, 8 loads in flight; 1 / 2: 2 / 1 in flight; 3: own launches
-  int gstore_direct = 0;            // sigma slabs leave the SM through st.global (A/B against the TMA-store path)
   // workspaces
   __nv_bfloat16* txt_all = nullptr;      // [world][Bmax, D] bf16; slot `rank` is what the peers pull (world > 1)
   __nv_bfloat16* G[kMaxWorld] = {};      // [Bp, Bp] sigma operands (fp16 bits x kGScale), diagonal zeroed, allocated on
@@ -334,7 +332,6 @@ void apply_aux(siglip_ctx* c, KernelParams& p, const AuxList& aux, const EndSign
     if (p.aux[i].sig_n > 0 || p.aux[i].done_flag != nullptr) p.aux[i].ticket = c->sync_words + i;
   }
   p.cvt_scale = kXScale;
-  p.cvt_inflight = (c->cvt_mode == 1) ? 2 : (c->cvt_mode == 2 ? 1 : 8);
   p.tprime_f64 = c->tprime_f64;
   p.pdl = c->pdl;
   p.peer_timeout_ns = peer_timeout_ns(c);
@@ -406,7 +403,6 @@ int run_loss_chunk(siglip_ctx* c, int gi, bool own, bool first, const void* img,
   p.dbg = c->dbg_dev;
   p.epi_sleep_ns = static_cast<unsigned int>(c->epi_sleep_loss_ns);
   if (save && c->dbg_no_gstore) p.store_g = 0;  // timing experiments only (wrong gradients)
-  if (save && c->gstore_direct && p.store_g) p.store_g = 1 + c->gstore_direct;   // st.global instead of TMA stores
   apply_aux(c, p, aux, end);
   unsigned long long* wstats = nullptr;
   if (c->dbg_loss_waitstats) {   // diagnostic: where the roles of the loss kernel spend their cycles
@@ -442,17 +438,8 @@ int run_loss_chunk(siglip_ctx* c, int gi, bool own, bool first, const void* img,
 
 // auxiliary jobs of a saving loss kernel: bf16 -> fp16 x 16 copies of the chunk's text (and, on the own chunk, of the
 // images) for the gradient kernel
-void add_cvt_jobs(siglip_ctx* c, AuxList& aux, int gi, bool own, const void* img, const __nv_bfloat16* txt_c, int Bn,
-                  cudaStream_t st) {
+void add_cvt_jobs(siglip_ctx* c, AuxList& aux, int gi, bool own, const void* img, const __nv_bfloat16* txt_c, int Bn) {
   if (c->dbg_no_cvt) return;
-  if (c->cvt_mode == 3) {   // measurement variant: the copies as launches of their own, in front of the loss kernel
-    siglip::launch_cvt16(txt_c, c->txt16[gi], static_cast<size_t>(Bn) * c->D * sizeof(__nv_bfloat16) / 16, kXScale,
-                         c->input_f16, c->num_sms, st);
-    if (own)
-      siglip::launch_cvt16(img, c->img16, static_cast<size_t>(c->B) * c->D * sizeof(__nv_bfloat16) / 16, kXScale,
-                           c->input_f16, c->num_sms, st);
-    return;
-  }
   siglip::AuxJob& jt = aux.add(siglip::kAuxCvt);
   jt.src = reinterpret_cast<const uint4*>(txt_c);
   jt.dst = reinterpret_cast<uint4*>(c->txt16[gi]);
@@ -682,7 +669,7 @@ int forward_impl(siglip_ctx* c, const void* img, const void* txt, const float* t
     const __nv_bfloat16* txt_c = (k == 0) ? own_txt : c->txt_all + cidx * stride;
     if (save && (rc = ensure_g(c, k))) return rc;
     AuxList aux;
-    if (save) add_cvt_jobs(c, aux, k, k == 0, img, txt_c, c->Bs[cidx], st);
+    if (save) add_cvt_jobs(c, aux, k, k == 0, img, txt_c, c->Bs[cidx]);
     if (k + 1 < W) {
       const int nxt = step_owner(c, r, k + 1);
       if (c->overlap_pull) {
@@ -860,7 +847,7 @@ int fused_impl(siglip_ctx* c, const void* img, const void* txt, const float* t_p
         if ((rc = signal_peers(c, 0, s, st))) return rc;
       }
     }
-    add_cvt_jobs(c, aux, 0, true, img, own_txt, c->B, st);
+    add_cvt_jobs(c, aux, 0, true, img, own_txt, c->B);
     if (W > 1) {
       if (ik) {
         // my contribution slots of the previous backward must have been read by their owners (flag 3) before G1
@@ -887,7 +874,7 @@ int fused_impl(siglip_ctx* c, const void* img, const void* txt, const float* t_p
     const __nv_bfloat16* txt_c = c->txt_all + cidx * stride;
     {
       AuxList aux;
-      add_cvt_jobs(c, aux, 1, false, img, txt_c, c->Bs[cidx], st);
+      add_cvt_jobs(c, aux, 1, false, img, txt_c, c->Bs[cidx]);
       if (k + 1 < W) add_pull_job(c, aux, step_owner(c, r, k + 1), s);
       const bool lastL = (k == W - 1);
       EndSignal end = (lastL && ik) ? end_signal(c, 2, s) : EndSignal();   // "I have pulled everyone's text"
@@ -1025,8 +1012,6 @@ static int ctx_create_impl(siglip_ctx** out, int device, int rank, int world, co
   c->Bp = round_up(Bmax, 256);
   c->dbg_no_gstore = getenv("SIGLIP_DEBUG_NO_GSTORE") != nullptr;
   c->dbg_no_cvt = getenv("SIGLIP_DEBUG_NO_CVT") != nullptr;
-  if (const char* e = getenv("SIGLIP_GSTORE_DIRECT")) c->gstore_direct = atoi(e);
-  if (const char* e = getenv("SIGLIP_CVT_MODE")) c->cvt_mode = atoi(e);
   c->dbg_loss_waitstats = getenv("SIGLIP_DEBUG_LOSS_WAITSTATS") != nullptr;
   if (const char* e = getenv("SIGLIP_INKERNEL_SYNC")) c->inkernel_sync = atoi(e) ? 1 : 0;   // A/B measurements
   if (const char* e = getenv("SIGLIP_SPLIT_K")) c->split_k = atoi(e);

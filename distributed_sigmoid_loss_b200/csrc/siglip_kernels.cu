@@ -270,57 +270,9 @@ struct GStore {
   int row0;                 // first row of this warp's 32-row block
   int lane;
   uint64_t policy;          // L2 evict_first: the sigma lines are not read again before they have left the L2
-  uint16_t* direct;         // non-null: the slab leaves the staging buffer through coalesced st.global instead of a TMA store
-  long long ldg;            // row pitch of the sigma buffer (elements), direct stores only
-  bool direct_regs;         // direct stores straight from the registers (no staging)
 };
 
 __device__ __forceinline__ void store_g_slab(const GStore& gs, int col0, const uint32_t (&packed)[16]) {
-  if (gs.direct != nullptr && gs.direct_regs) {
-    // Variant without shared memory at all: every lane writes the 64 bytes of its own row (4 x 16 B, rows ldg apart)
-    if (gs.row0 + gs.lane < gs.ldg) {
-      uint16_t* dst = gs.direct + static_cast<long long>(gs.row0 + gs.lane) * gs.ldg + col0;
-#pragma unroll
-      for (int c = 0; c < 4; ++c)
-        asm volatile("st.global.L2::cache_hint.v4.b32 [%0], {%1, %2, %3, %4}, %5;" ::"l"(dst + 8 * c),
-                     "r"(packed[4 * c + 0]), "r"(packed[4 * c + 1]), "r"(packed[4 * c + 2]), "r"(packed[4 * c + 3]),
-                     "l"(gs.policy)
-                     : "memory");
-    }
-    return;
-  }
-  if (gs.direct != nullptr) {
-    // Variant without the TMA engine: transpose through the staging buffer and write 8 rows x 64 contiguous bytes per
-    // instruction (4 lanes per row segment). A TMA store of a {32 x 64 B} box is paced by its 32 row requests.
-    __syncwarp();                                         // the previous slab's reads of the staging buffer are done
-    const uint32_t row_addr = gs.stage + static_cast<uint32_t>(gs.lane) * 64u;
-    const uint32_t sw = (static_cast<uint32_t>(gs.lane) >> 1) & 3u;
-#pragma unroll
-    for (uint32_t c = 0; c < 4; ++c) {
-      asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(row_addr + ((c ^ sw) << 4)), "r"(packed[4 * c + 0]),
-                   "r"(packed[4 * c + 1]), "r"(packed[4 * c + 2]), "r"(packed[4 * c + 3])
-                   : "memory");
-    }
-    __syncwarp();
-    const uint32_t cc = static_cast<uint32_t>(gs.lane) & 3u;
-    uint16_t* gcol = gs.direct + col0 + 8 * static_cast<int>(cc);
-#pragma unroll
-    for (uint32_t i = 0; i < 4; ++i) {
-      const uint32_t r = 8u * i + (static_cast<uint32_t>(gs.lane) >> 2);
-      uint32_t a, b, c2, d;
-      asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
-                   : "=r"(a), "=r"(b), "=r"(c2), "=r"(d)
-                   : "r"(gs.stage + r * 64u + ((cc ^ ((r >> 1) & 3u)) << 4))
-                   : "memory");
-      uint16_t* dst = gcol + static_cast<long long>(gs.row0 + static_cast<int>(r)) * gs.ldg;
-      // the buffer is square [ldg, ldg], padded to whole tiles; only a fully masked tile of a multicast cluster lies outside
-      if (gs.row0 + static_cast<int>(r) < gs.ldg)
-        asm volatile("st.global.L2::cache_hint.v4.b32 [%0], {%1, %2, %3, %4}, %5;" ::"l"(dst), "r"(a), "r"(b), "r"(c2),
-                     "r"(d), "l"(gs.policy)
-                     : "memory");
-    }
-    return;
-  }
   // the previous TMA store of this warp must have finished READING the staging buffer
   if (gs.lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
   __syncwarp();
@@ -856,9 +808,6 @@ siglip_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_consta
       gst.row0 = tc.m_blk * C::kTileM + static_cast<int>(cta_rank) * kBlockM + q * 32;
       gst.lane = lane;
       gst.policy = g_store_policy;
-      gst.direct = (kMode == kModeLoss && p.store_g >= 2) ? reinterpret_cast<uint16_t*>(p.G) : nullptr;
-      gst.direct_regs = p.store_g == 3;
-      gst.ldg = p.ldg;
       float scale = 0.f, fix = 0.f;
       if constexpr (kMode == kModeLoss) {
         const int tile_m0 = tc.m_blk * C::kTileM, tile_n0 = tc.n_blk * kTileN;
@@ -1174,20 +1123,12 @@ siglip_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_consta
         // 8 independent 16-byte loads in flight per thread: with one the loop was latency-bound (0.26 ms for the two
         // 32 MiB operands of the headline shape, most of the loss kernel's duration, for 128 MiB of traffic)
         unsigned long long i = tid0;
-        if (p.cvt_inflight == 2) {          // measurement variant: a quarter of the memory-level parallelism
-          for (; i + nthreads < n16; i += 2ull * nthreads) {
-            const uint4 v0 = ld_peer_16(job.src + i), v1 = ld_peer_16(job.src + i + nthreads);
-            job.dst[i] = cvt(v0);
-            job.dst[i + nthreads] = cvt(v1);
-          }
-        } else if (p.cvt_inflight != 1) {
-          for (; i + 7ull * nthreads < n16; i += 8ull * nthreads) {
-            uint4 v[8];
+        for (; i + 7ull * nthreads < n16; i += 8ull * nthreads) {
+          uint4 v[8];
 #pragma unroll
-            for (int u = 0; u < 8; ++u) v[u] = ld_peer_16(job.src + i + u * nthreads);
+          for (int u = 0; u < 8; ++u) v[u] = ld_peer_16(job.src + i + u * nthreads);
 #pragma unroll
-            for (int u = 0; u < 8; ++u) job.dst[i + u * nthreads] = cvt(v[u]);
-          }
+          for (int u = 0; u < 8; ++u) job.dst[i + u * nthreads] = cvt(v[u]);
         }
         for (; i < n16; i += nthreads) job.dst[i] = cvt(ld_peer_16(job.src + i));
       } else if (job.kind == kAuxFold) {
@@ -1312,34 +1253,6 @@ __global__ void scale_kernel(const void* __restrict__ src, void* __restrict__ ds
       reinterpret_cast<float*>(dst)[i] = reinterpret_cast<const float*>(src)[i] * s;
     }
   }
-}
-
-// bf16 -> fp16 x scale (or plain copy) of an embedding matrix as a launch of its own: the measurement variant of the
-// auxiliary conversion jobs of the loss kernel (SIGLIP_CVT_MODE=3)
-__global__ void cvt16_kernel(const uint4* __restrict__ src, uint4* __restrict__ dst, unsigned long long n16, float sc,
-                             int plain) {
-  const unsigned long long nthreads = static_cast<unsigned long long>(gridDim.x) * blockDim.x;
-  unsigned long long i = static_cast<unsigned long long>(blockIdx.x) * blockDim.x + threadIdx.x;
-  auto cvt = [&](uint4 v) {
-    if (plain) return v;
-    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
-    uint32_t o[4];
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      const float lo = fminf(fmaxf(__uint_as_float(w[q] << 16) * sc, -65504.f), 65504.f);
-      const float hi = fminf(fmaxf(__uint_as_float(w[q] & 0xffff0000u) * sc, -65504.f), 65504.f);
-      o[q] = pack_16x2<true>(lo, hi);
-    }
-    return make_uint4(o[0], o[1], o[2], o[3]);
-  };
-  for (; i + 3ull * nthreads < n16; i += 4ull * nthreads) {
-    uint4 v[4];
-#pragma unroll
-    for (int u = 0; u < 4; ++u) v[u] = ld_peer_16(src + i + u * nthreads);
-#pragma unroll
-    for (int u = 0; u < 4; ++u) dst[i + u * nthreads] = cvt(v[u]);
-  }
-  for (; i < n16; i += nthreads) dst[i] = cvt(ld_peer_16(src + i));
 }
 
 __global__ void signal_flags_kernel(unsigned int* const* flag_ptrs, int n, unsigned int value) {
@@ -1780,12 +1693,6 @@ int launch_scale(const void* src, void* dst, int is_bf16, const float* g, size_t
                  cudaStream_t stream) {
   const int aligned = ((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst)) & 15u) == 0;
   scale_kernel<<<num_sms * 4, 256, 0, stream>>>(src, dst, is_bf16, g, nbytes, aligned);
-  return static_cast<int>(cudaGetLastError());
-}
-
-int launch_cvt16(const void* src, void* dst, size_t n16, float scale, int plain, int num_sms, cudaStream_t stream) {
-  cvt16_kernel<<<num_sms * 4, 256, 0, stream>>>(reinterpret_cast<const uint4*>(src), reinterpret_cast<uint4*>(dst),
-                                                static_cast<unsigned long long>(n16), scale, plain);
   return static_cast<int>(cudaGetLastError());
 }
 

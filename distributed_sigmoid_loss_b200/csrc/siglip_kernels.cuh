@@ -98,7 +98,6 @@ struct KernelParams {
   AuxJob aux[kMaxAuxJobs];
   int naux;
   float cvt_scale;   // kAuxCvt: dst = fp16(src_bf16 * cvt_scale), clamped
-  int cvt_inflight;  // kAuxCvt: 16-byte loads in flight per thread: 0 / 8 (default), 2 or 1 (measurement variants)
   // Signal written when the LAST CTA of the launch has finished (ticket counter): everything this launch wrote is then
   // visible to the peers that observe the flag (st.release.sys after a system-scope fence).
   unsigned int* const* end_sig_ptrs;   // device array of flag addresses (peer-mapped), null = no signal
@@ -157,9 +156,6 @@ int launch_normalize_bwd(const void* x, int in_bf16, const float* inv_norm, cons
 // dst = src * (*g) over nbytes (multiple of 16) of fp32 or bf16 data
 int launch_scale(const void* src, void* dst, int is_bf16, const float* g, size_t nbytes, int num_sms,
                  cudaStream_t stream);
-
-// dst = fp16(src_bf16 * scale) (or a plain 16-byte copy) over n16 16-byte vectors, as a launch of its own
-int launch_cvt16(const void* src, void* dst, size_t n16, float scale, int plain, int num_sms, cudaStream_t stream);
 
 // cross-rank flag helpers (peer-mapped pointers)
 int launch_allreduce_scalars(const float* saved, const float* g, float* mailbox_local, const float* const* mailboxes_dev,
