@@ -139,6 +139,36 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, DebugRe
   if (waited) *waited += clock_cycles() - c0;
 }
 
+// The same wait for a warp whose 32 lanes all poll (warp-uniform loops of the TMA producer / MMA issuer): the warp
+// votes on the outcome, so the control flow around the wait is uniform for the compiler as well and the loop's
+// counters, barrier addresses and descriptors can stay in uniform registers.
+__device__ __forceinline__ void mbar_wait_warp(uint32_t bar, uint32_t parity, DebugRecord* dbg, uint32_t site,
+                                               uint32_t aux0 = 0, uint32_t aux1 = 0, long long* waited = nullptr) {
+  if (__all_sync(0xffffffffu, mbar_try_wait(bar, parity))) return;
+  const long long c0 = waited ? clock_cycles() : 0;
+  uint64_t t0 = 0;
+  uint32_t spins = 0;
+  while (!__all_sync(0xffffffffu, mbar_try_wait(bar, parity))) {
+    if ((++spins & 0x3ffu) == 0) {
+      uint64_t now = globaltimer_ns();
+      if (t0 == 0) t0 = now;
+      if (now - t0 > SIGLIP_WAIT_TIMEOUT_NS) {
+        if (dbg != nullptr) {
+          dbg->block = blockIdx.x;
+          dbg->thread = threadIdx.x;
+          dbg->aux0 = aux0;
+          dbg->aux1 = aux1;
+          dbg->aux2 = parity;
+          dbg->code = site;
+          __threadfence_system();
+        }
+        __trap();
+      }
+    }
+  }
+  if (waited) *waited += clock_cycles() - c0;
+}
+
 // ---------------------------------------------------------------------------------------------
 // TMA
 // ---------------------------------------------------------------------------------------------

@@ -646,7 +646,7 @@ siglip_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_consta
       uint32_t phase = 0;
       int as = 0;
       uint32_t aphase = 0;
-      long long w_full = 0, w_tmem = 0, w_issue = 0, w_commit = 0;
+      long long w_full = 0, w_tmem = 0;
       const bool prof = p.wait_stats != nullptr;
       const long long c_start = clock_cycles();
       for (int t = cluster_id; t < total_tiles; t += num_clusters) {
@@ -674,49 +674,49 @@ siglip_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_consta
         }
         // The k loop is the critical path of the kernel (one elected lane feeds the tensor pipe): keep it free of
         // anything that is not the four MMAs and the two commits. The 8-bit measurement variant gets its own copy.
+        // Everything the four MMAs of a k block need is computed here, in warp-uniform code (uniform registers), from
+        // 32-bit arithmetic on the low descriptor word (the start-address field cannot carry out of it: shared memory
+        // addresses >> 4 stay below 2^14); the elected branch holds nothing but the issue. This warp shares its
+        // scheduler with four epilogue warps: in the loss kernel (busy epilogue) every instruction of this loop shows
+        // up as tensor-pipe idle time (138 instead of 128 cycles per MMA with the ~96-instruction loop this replaces).
+        const uint32_t a_hi = static_cast<uint32_t>(adesc0 >> 32), b_hi = static_cast<uint32_t>(bdesc0 >> 32);
+        const uint32_t a_lo0 = static_cast<uint32_t>(adesc0), b_lo0 = static_cast<uint32_t>(bdesc0);
+        auto desc64 = [](uint32_t hi, uint32_t lo) { return (static_cast<uint64_t>(hi) << 32) | lo; };
         auto issue_tile = [&](auto is_fp8) {
           for (int kb = kb0; kb < kb1; ++kb) {
-            mbar_wait(full_bar(stage), phase, p.dbg, 3, t, kb, 0, prof ? &w_full : nullptr);
+            mbar_wait_warp(full_bar(stage), phase, p.dbg, 3, t, kb, prof ? &w_full : nullptr);
             tc_fence_after();
-            const long long c0 = prof ? clock_cycles() : 0;
-            long long c1 = 0;
+            const uint32_t so = static_cast<uint32_t>(stage) * static_cast<uint32_t>(C::kStageBytes >> 4);
+            const uint32_t al = a_lo0 + so, bl = b_lo0 + so;
+            const uint32_t acc0 = static_cast<uint32_t>(kb != kb0);
+            const bool last = (kb == kb1 - 1);
+            const uint32_t ebar = empty_bar(stage);
             if (elect_one_sync()) {
-              const uint64_t adesc = adesc0 + static_cast<uint64_t>(stage * (C::kStageBytes >> 4));
-              const uint64_t bdesc = bdesc0 + static_cast<uint64_t>(stage * (C::kStageBytes >> 4));
 #pragma unroll
               for (int k = 0; k < kBlockK / kUmmaK; ++k) {
+                const uint64_t ad = desc64(a_hi, al + static_cast<uint32_t>(k) * a_adv);
+                const uint64_t bd = desc64(b_hi, bl + static_cast<uint32_t>(k) * b_adv);
                 if constexpr (decltype(is_fp8)::value) {   // kind::f8f6f4: 32 e4m3 values (32 bytes) per instruction
-                  umma_f8<kCG>(tmem_d, adesc + static_cast<uint64_t>(k * a_adv),
-                               bdesc + static_cast<uint64_t>(k * b_adv), idesc,
-                               static_cast<uint32_t>(kb != kb0 || k != 0));
+                  umma_f8<kCG>(tmem_d, ad, bd, idesc, k == 0 ? acc0 : 1u);
                 } else {
-                  umma_bf16<kCG>(tmem_d, adesc + static_cast<uint64_t>(k * a_adv),
-                                 bdesc + static_cast<uint64_t>(k * b_adv), idesc,
-                                 static_cast<uint32_t>(kb != kb0 || k != 0));
+                  umma_bf16<kCG>(tmem_d, ad, bd, idesc, k == 0 ? acc0 : 1u);
                 }
               }
-              c1 = prof ? clock_cycles() : 0;
               if constexpr (kMC > 1 && kCG == 1) {
-                umma_commit_mcast(empty_bar(stage), kMcMask);  // stage is free in every CTA that writes into it
+                umma_commit_mcast(ebar, kMcMask);  // stage is free in every CTA that writes into it
               } else if constexpr (kMC > 1) {
-                umma_commit_2sm_mask(empty_bar(stage), kMcMask);   // all four CTAs of the 2x2 cluster
+                umma_commit_2sm_mask(ebar, kMcMask);   // all four CTAs of the 2x2 cluster
               } else {
-                umma_commit<kCG>(empty_bar(stage));  // frees the smem stage (both CTAs) when the MMAs retire
+                umma_commit<kCG>(ebar);  // frees the smem stage (both CTAs) when the MMAs retire
               }
-              if (kb == kb1 - 1) {                   // accumulator ready for the epilogue warps of this pair
+              if (last) {                            // accumulator ready for the epilogue warps of this pair
                 if constexpr (kMC > 1 && kCG == 2) {
                   umma_commit_2sm_mask(tmem_full_bar(as), static_cast<uint16_t>(0x3u << leader_rank));
                 } else {
                   umma_commit<kCG>(tmem_full_bar(as));
                 }
               }
-              if (prof) {
-                const long long c2 = clock_cycles();
-                w_issue += c1 - c0;
-                w_commit += c2 - c1;
-              }
             }
-            __syncwarp();
             if (++stage == C::kStages) {
               stage = 0;
               phase ^= 1u;
@@ -738,17 +738,10 @@ siglip_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_consta
         atomicMax(p.aux_trace + 9, now);                              // ... latest / earliest over the issuing CTAs
         atomicMin(p.aux_trace + 10, now);
       }
-      if (prof) {
-        // the elected lane accumulated issue/commit; every lane has the (identical) wait counters
-        const long long wi = __reduce_max_sync(0xffffffffu, static_cast<int>(w_issue >> 8));
-        const long long wc = __reduce_max_sync(0xffffffffu, static_cast<int>(w_commit >> 8));
-        if (lane == 0) {
-          p.wait_stats[8ll * blockIdx.x + 1] = static_cast<unsigned long long>(w_full);
-          p.wait_stats[8ll * blockIdx.x + 2] = static_cast<unsigned long long>(w_tmem);
-          p.wait_stats[8ll * blockIdx.x + 3] = static_cast<unsigned long long>(clock_cycles() - c_start);
-          p.wait_stats[8ll * blockIdx.x + 4] = static_cast<unsigned long long>(wi << 8);
-          p.wait_stats[8ll * blockIdx.x + 5] = static_cast<unsigned long long>(wc << 8);
-        }
+      if (prof && lane == 0) {
+        p.wait_stats[8ll * blockIdx.x + 1] = static_cast<unsigned long long>(w_full);
+        p.wait_stats[8ll * blockIdx.x + 2] = static_cast<unsigned long long>(w_tmem);
+        p.wait_stats[8ll * blockIdx.x + 3] = static_cast<unsigned long long>(clock_cycles() - c_start);
       }
     }
   } else if (warp < kNumEpiWarps) {
