@@ -2,12 +2,12 @@ set -x
 export SIGLIP_PEER_TIMEOUT_MS=30000
 N=${1:-8}
 TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1"
-timeout 400 $TR --master-port 29611 tools/multi_gpu_check.py 2>&1 | grep -v "^W0\|^\*\*\*\|UserWarning\|Consider using\|loss=abs\|OMP_NUM" > gpurun_out/r02_multi_gpu_check_n$N.log
-tail -2 gpurun_out/r02_multi_gpu_check_n$N.log; grep -c " OK" gpurun_out/r02_multi_gpu_check_n$N.log; grep -c "FAIL" gpurun_out/r02_multi_gpu_check_n$N.log
-timeout 300 $TR --master-port 29613 bench.py --gpus $N --steps 20 --warmup 5 2>gpurun_out/r02_bench_n$N.err > gpurun_out/r02_bench_n$N.json
+timeout 400 $TR --master-port 29611 tools/multi_gpu_check.py 2>&1 | grep -v "^W0\|^\*\*\*\|UserWarning\|Consider using\|loss=abs\|OMP_NUM" > gpurun_out/r02f_multi_gpu_check_n$N.log
+tail -2 gpurun_out/r02f_multi_gpu_check_n$N.log; grep -c " OK" gpurun_out/r02f_multi_gpu_check_n$N.log; grep -c "FAIL" gpurun_out/r02f_multi_gpu_check_n$N.log
+timeout 300 $TR --master-port 29613 bench.py --gpus $N --steps 20 --warmup 5 2>gpurun_out/r02f_bench_n$N.err > gpurun_out/r02f_bench_n$N.json
 python - <<PY
 import json
-for f in ("gpurun_out/r02_bench_n$N.json",):
+for f in ("gpurun_out/r02f_bench_n$N.json",):
     try:
         d=json.loads(open(f).read().strip().splitlines()[-1])
     except Exception as e:
@@ -19,4 +19,4 @@ for f in ("gpurun_out/r02_bench_n$N.json",):
     if d.get("parity"): print("   parity", d["parity"]["fused_fp32"])
     print("   nvlink", d.get("nvlink"))
 PY
-tail -c 300 gpurun_out/r02_bench_n$N.err
+tail -c 300 gpurun_out/r02f_bench_n$N.err
