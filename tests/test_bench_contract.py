@@ -61,6 +61,7 @@ def test_product_arm_line():
     assert r["bound"] == "tensor" and r["unit"] == "TFLOP/s" and 0 < r["frac"] < 1.2 and r["launches_timed"] == 3
     e = d["e2e"]
     assert e["h2d_bytes_per_step"] == 2 * 2048 * 256 * 2 and e["d2h_bytes_per_step"] == 12 and e["value"] > 0
+    assert e["first_steps_ms_per_step"] > 0 and "sustained" in e["api"]   # the headline e2e figure is the sustained one
     g = e["with_grads"]
     assert g["d2h_bytes_per_step"] == 2 * 2048 * 256 * 2 + 12 and g["value"] > 0 and g["loss"] == e["loss"]
     assert d["cpu_baseline"]["kind"] in ("reference", "port") and d["cpu_baseline"]["value"] > 0

@@ -220,3 +220,37 @@ def test_buffer_reuse_waits_are_implied_by_the_data_dependencies():
                 simulate(world, steps=4, bidir=(seed % 2 == 1), seed=seed, lag_rank=seed % world)
     finally:
         globals()["build_actions"] = orig
+
+
+def test_loss_epilogue_slab_classes_cover_exactly_the_special_elements():
+    """CPU model of the per-slab path choice of the loss epilogue (csrc/siglip_kernels.cu, `slab_diag` / `slab_edge`):
+    a 32x32 slab whose first row and first column are multiples of 32 holds positive pairs (row == col, own chunk) iff
+    row0 == col0, and holds masked elements (row >= M or col >= N) iff it crosses the border — for every tile shape of
+    cta_group 1 (128x256) and 2 (256x256), aligned and ragged batches, including the fully masked extra tile of an odd
+    tile row under multicast. Everything else may take the fast path, which applies neither labels nor masks."""
+    for cg in (1, 2):
+        tile_m = 128 * cg
+        for (M, N) in [(256, 256), (512, 512), (300, 136), (1000, 1000), (40, 24), (1024, 520)]:
+            tiles_m, tiles_n = -(-M // tile_m), -(-N // 256)
+            for m_blk in range(tiles_m + 1):          # + 1: the fully masked tile a 2-tile cluster may be handed
+                for n_blk in range(tiles_n):
+                    tile_m0, tile_n0 = m_blk * tile_m, n_blk * 256
+                    edge = (tile_m0 + tile_m > M) or (tile_n0 + 256 > N)
+                    diag = (tile_m0 < tile_n0 + 256) and (tile_n0 < tile_m0 + tile_m)
+                    for cta_rank in range(cg):
+                        for q in range(4):
+                            row0 = tile_m0 + cta_rank * 128 + q * 32
+                            for cgrp in range(4):
+                                for c in range(2):
+                                    col0 = tile_n0 + cgrp * 64 + c * 32
+                                    has_pos = any(row0 + l == col0 + j for l in range(32) for j in range(32)
+                                                  if row0 + l < M and col0 + j < N)
+                                    has_masked = (row0 + 32 > M) or (col0 + 32 > N)
+                                    slab_diag = diag and row0 == col0
+                                    slab_edge = edge and ((row0 + 32 > M) or (col0 + 32 > N))
+                                    assert slab_edge == has_masked
+                                    # a slab with positives is always routed to the general path
+                                    assert (not has_pos) or slab_diag or slab_edge
+                                    # and a slab routed to the fast path has neither positives nor masked elements
+                                    if not (slab_diag or slab_edge):
+                                        assert not has_pos and not has_masked
