@@ -864,7 +864,7 @@ siglip_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_consta
             else
               loss_slab<false, false, true>(v, t_eff, bias, row, col0, pr.M, pr.N, sg, gst, p.g_scale, p.g_diag, acc_sp, acc_g, acc_gs);
           } else {
-            // edge and / or diagonal tiles (a few per chunk): ONE masked variant — two more copies of the unrolled
+            // border and / or diagonal slabs (a few per chunk): ONE masked variant — two more copies of the unrolled
             // general path only made the kernel's code larger (the loss and gradient kernels alternate and share the
             // instruction caches)
             loss_slab<true, true, true>(v, t_eff, bias, row, col0, pr.M, pr.N, sg, gst, p.g_scale, p.g_diag, acc_sp, acc_g, acc_gs, slab_diag);
